@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- Phi a + Phi^T r matvec pairs/s of the outerbase hot path (BASELINE.json metric).
+
+Workload (config C3 of BASELINE.json): wing-weight-style d=10 inputs, N = 1,000,000 rows in
+total, K = 2000 terms from selectterms, `mat25pow` covariances with 40 quantile knots per
+dimension, spread hyper-parameters.  With --gpus G the N rows are sharded over G ranks
+(strong scaling) and every Phi^T r ends in one NCCL allreduce of K doubles.
+
+A "step" is one CG iteration's worth of the path (src/fit.cpp:71-85): two (Phi a, Phi^T r)
+pairs.  `value` is pairs/s with every operand resident in HBM (device-pointer C ABI), timed
+with CUDA events on the library's stream, max over ranks.  `e2e` is the same metric through
+the reference-facing calls outerbase::mm / outerbase::tmm with HOST buffers (coefficients and
+residuals copied in, results copied out, every call).  `--impl reference` times the CPU
+oracle's OpenMP restatement of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+D, N_TOTAL, K_TERMS, KNOTS = 10, 1_000_000, 2000, 40
+
+
+def synth_rows(lo: int, hi: int, d: int, seed: int = 42) -> np.ndarray:
+    """Rows [lo, hi) of the synthetic U(0,1)^d design; identical for any sharding."""
+    blk = 1 << 16
+    out = np.empty((hi - lo, d), order="F")
+    b0 = lo // blk
+    pos = 0
+    while pos < hi - lo:
+        start = b0 * blk
+        rng = np.random.default_rng([seed, b0])
+        chunk = rng.uniform(size=(blk, d))
+        a = max(lo, start) - start
+        b = min(hi, start + blk) - start
+        out[pos:pos + (b - a)] = chunk[a:b]
+        pos += b - a
+        b0 += 1
+    return out
+
+
+def wingweight(x: np.ndarray) -> np.ndarray:
+    """Wing-weight-style 10-input closed form (Forrester et al. 2008), inputs scaled from [0,1]."""
+    Sw = 150 + 50 * x[:, 0]; Wfw = 220 + 80 * x[:, 1]; A = 6 + 4 * x[:, 2]
+    Lam = (-10 + 20 * x[:, 3]) * np.pi / 180; q = 16 + 29 * x[:, 4]; lam = 0.5 + 0.5 * x[:, 5]
+    tc = 0.08 + 0.1 * x[:, 6]; Nz = 2.5 + 3.5 * x[:, 7]; Wdg = 1700 + 800 * x[:, 8]; Wp = 0.025 + 0.055 * x[:, 9]
+    return (0.036 * Sw ** 0.758 * Wfw ** 0.0035 * (A / np.cos(Lam) ** 2) ** 0.6 * q ** 0.006 * lam ** 0.04
+            * (100 * tc / np.cos(Lam)) ** (-0.3) * (Nz * Wdg) ** 0.49 + Sw * Wp)
+
+
+def setup_model(lib, d=D, K=K_TERMS):
+    """outermod with the obfit defaults (R/fitting.R:66-75): mat25pow, 40 quantile knots per dim."""
+    om = lib.outermod()
+    om.setcovfs(["mat25pow"] * d)
+    sample = synth_rows(0, 100_000, d)
+    q = np.linspace(0, 1, KNOTS) * KNOTS / (KNOTS + 1) + 0.5 / (KNOTS + 1)  # .genknotlist, R/fitting.R:177-185
+    om.setknot([np.quantile(sample[:, l], q) for l in range(d)])
+    hyp = om.gethyp()
+    hyp[0::2] = np.linspace(-0.6, 0.4, d)  # anisotropic terms
+    om.updatehyp(hyp)
+    terms = om.selectterms(K)
+    return om, terms
+
+
+def term_stats(terms):
+    nnz = (terms > 0).sum(1)
+    return int((nnz + 1).sum()), int(terms.max(0).sum())
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+        self.t0 = self.t1 = None
+
+    def mark(self, which):
+        setattr(self, which, time.time())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(", ") for r in Path(self.f.name).read_text().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except Exception:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        # the sampler runs across the whole bench; the under-load clock is the top half of the samples
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_lib():
+    from outerbase_b200.binding import Library
+    so = REPO / "oracle" / "_build" / "libob_oracle.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(REPO / "oracle")], check=True, capture_output=True)
+    return Library(so, "orc_")
+
+
+def cpu_pairs_per_s(sample_rows: int, steps: int, warmup: int, budget_s: float = 25.0):
+    """The oracle's OpenMP restatement of prodmm_/tprodmm_ on a row sample; scaled to N_TOTAL rows."""
+    O = oracle_lib()
+    om, terms = setup_model(O)
+    x = synth_rows(0, sample_rows, D)
+    ob = O.outerbase(om, x, dograd=False)
+    rng = np.random.default_rng(1)
+    a = np.sqrt(om.getvar(terms) / 20) * rng.normal(size=K_TERMS)
+    r = rng.normal(size=sample_rows)
+    cores = ob.nthreads
+    for _ in range(max(1, warmup)):
+        ob.matmul(terms, a); ob.tmatmul(terms, r)
+    t0 = time.time()
+    done = 0
+    for _ in range(steps):
+        for _ in range(2):
+            ob.matmul(terms, a); ob.tmatmul(terms, r)
+        done += 1
+        if time.time() - t0 > budget_s:
+            break
+    dt = time.time() - t0
+    pairs_sample = 2 * done / dt
+    return pairs_sample * sample_rows / N_TOTAL, cores, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 50_000
+    val, cores, done, dt = cpu_pairs_per_s(sample, args.steps, args.warmup, budget_s=60.0)
+    W, Lcols = None, None
+    line = {
+        "impl": "reference", "metric": "phi_matvec_pairs_per_s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1) * (N_TOTAL / sample),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 wingweight-style d={D} N={N_TOTAL} K={K_TERMS} mat25pow 40 knots/dim (timed on a {sample}-row sample, scaled)"},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": int(cores), "kind": "port",
+                         "sample": f"{sample} of {N_TOTAL} rows, {done} steps of 2 pairs, OpenMP row-chunk path of the oracle (-O2)"},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_TOTAL, help="total rows over all ranks")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optcg", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    import outerbase_b200 as obp
+    if not obp.LIBPATH.exists():
+        obp.build()
+    lib = obp.lib(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        lib.comm_init(world, rank, box[0])
+
+    N = args.rows
+    lo, hi = (N * rank) // world, (N * (rank + 1)) // world
+    nloc = hi - lo
+    om, terms = setup_model(lib)
+    W, Lcols = term_stats(terms)
+    x = synth_rows(lo, hi, D)
+    y_all_scale = None
+    ob = lib.outerbase(om, x, dograd=False)
+    ob.set_terms(terms)
+    rng = np.random.default_rng(1)
+    a_h = np.sqrt(om.getvar(terms) / 20) * rng.normal(size=K_TERMS)
+    r_h = np.random.default_rng([7, rank]).normal(size=nloc)
+
+    stream = torch.cuda.ExternalStream(lib.stream())
+    dev = torch.device("cuda", local)
+    a_d = torch.from_numpy(a_h).to(dev)
+    r_d = torch.from_numpy(r_h).to(dev)
+    yhat_d = torch.empty(((nloc + 127) // 128) * 128, dtype=torch.float64, device=dev)
+    g_d = torch.empty(K_TERMS, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_dev(ev=None):
+        for i in range(2):
+            if ev is not None: ev[0][i].record(stream)
+            ob.mm_dev(a_d.data_ptr(), yhat_d.data_ptr())
+            if ev is not None: ev[1][i].record(stream)
+            ob.tmm_dev(r_d.data_ptr(), g_d.data_ptr())
+            if ev is not None: ev[2][i].record(stream)
+
+    def barrier():
+        lib.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    fp64_peak = lib.fp64_peak()
+    clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    # ---- value: device-resident operands
+    evs = [[[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.launch_count()
+    e0.record(stream)
+    for s in range(args.steps):
+        step_dev(evs[s])
+    e1.record(stream)
+    barrier()
+    launches = lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    t_a = float(np.mean([evs[s][0][i].elapsed_time(evs[s][1][i]) for s in range(args.steps) for i in range(2)]))
+    t_t = float(np.mean([evs[s][1][i].elapsed_time(evs[s][2][i]) for s in range(args.steps) for i in range(2)]))
+    tms = torch.tensor([ms, t_a, t_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, t_a, t_t = [float(v) for v in tms.cpu()]
+    value = 2 * args.steps / (ms * 1e-3)
+
+    # ---- e2e: reference-facing calls with host buffers, pinned staging inside the library
+    for _ in range(2):
+        ob.matmul(terms, a_h); ob.tmatmul(terms, r_h)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        for _ in range(2):
+            yh = ob.matmul(terms, a_h)
+            gh = ob.tmatmul(terms, r_h)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = 2 * e2e_steps / float(dt.cpu()[0])
+    h2d = 2 * (K_TERMS * 8 + nloc * 8)
+    d2h = 2 * (nloc * 8 + K_TERMS * 8)
+
+    # ---- obfit's CG solve on the same shard: lpdfvec(logpr_gauss, loglik_gauss).optcg(0.001, 100)
+    optcg = None
+    if not args.no_optcg:
+        yv = wingweight(x)
+        stats = torch.tensor([yv.sum(), (yv ** 2).sum(), float(nloc)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(stats)
+        s1, s2, n = [float(v) for v in stats.cpu()]
+        mean = s1 / n
+        sd = np.sqrt((s2 - n * mean * mean) / (n - 1))
+        yv = (yv - mean) / sd
+        logpr = lib.logpr_gauss(om, terms)
+        loglik = lib.loglik_gauss(om, terms, yv, x)
+        vec = lib.lpdfvec(logpr, loglik)  # prior first, as obfit does (R/fitting.R:86,107)
+        barrier()
+        t0 = time.perf_counter()
+        vec.optcg(0.001, 100)
+        barrier()
+        t_cg = time.perf_counter() - t0
+        optcg = {"wall_s": t_cg, "iters": vec.cg_iters, "val": vec.val, "pairs": 2 * vec.cg_iters + 2}
+        del vec, loglik, logpr
+
+    clk = clocks.stop() if clocks else None
+    if rank == 0:
+        hbm_peak, hbm_src = 6650.0, "fallback"
+        mp = REPO / "MEASURED_PEAKS.json"
+        if mp.exists():
+            hbm_peak, hbm_src = float(json.loads(mp.read_text())["hbm_gbs"]), "measured"
+        # dominant kernel: the slower of the two Phi kernels; algorithmic work N*W flop (+N), SURVEY 8d
+        dom, t_dom = ("phi_t_kernel", t_t) if t_t >= t_a else ("phi_a_kernel", t_a)
+        nmax = -(-N // world)
+        flop = nmax * (W + 1)
+        achieved = flop / (t_dom * 1e-3) / 1e12
+        bytes_alg = nmax * 8 * (Lcols + 1) + nmax * 8
+        roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                    "peak_source": "DFMA micro-benchmark run in this process (nominal 37.2 TFLOP/s at 1965 MHz)",
+                    "algorithmic_flop_per_launch": flop, "W": W, "Lcols": Lcols,
+                    "ms_phi_a": t_a, "ms_phi_t": t_t,
+                    "hbm": {"achieved_gbs": bytes_alg / (t_dom * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                            "algorithmic_bytes_per_launch": bytes_alg}}
+        line = {
+            "metric": "phi_matvec_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 wingweight-style d={D} N={N} K={K_TERMS} mat25pow {KNOTS} knots/dim, rows sharded over {world} GPU(s)",
+                       "step": "one CG iteration of fit.cpp:71-85 = 2 x (Phi a, Phi^T r [+allreduce])",
+                       "l2": f"inputs exceed L2: {nmax * 8 * (Lcols + 2) / 1e6:.0f} MB of basis columns per pass vs 126 MB"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk, "optcg": optcg,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sample = 20_000
+                v, cores, done, dtc = cpu_pairs_per_s(sample, 8, 1, budget_s=20.0)
+                line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": int(cores), "kind": "port",
+                                        "sample": f"{sample} of {N} rows, {done} steps of 2 pairs in {dtc:.1f} s, scaled by rows"}
+            except Exception as e:  # the oracle is only the reported baseline
+                line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

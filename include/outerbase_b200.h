@@ -61,6 +61,8 @@ int ob_ctx_stream(ob_ctx* ctx, void** stream_out);
 int ob_comm_get_unique_id(void* id128);
 int ob_ctx_comm_init(ob_ctx* ctx, int nranks, int rank, const void* id128);
 int ob_ctx_comm_info(ob_ctx* ctx, int* nranks, int* rank);
+/* measured FP64 FMA peak of this GPU (TFLOP/s): the roofline denominator bench.py quotes. */
+int ob_ctx_fp64_peak(ob_ctx* ctx, double* tflops);
 /* test hook: number of CUDA kernels this context has launched so far. */
 int ob_ctx_launch_count(ob_ctx* ctx, uint64_t* count);
 
@@ -120,6 +122,10 @@ int ob_outerbase_build(ob_outerbase* ob);
 int ob_outerbase_set_nthreads(ob_outerbase* ob, int nthreads);
 int ob_outerbase_loopvals(ob_outerbase* ob, uint64_t* nthreads, uint64_t* chunksize,
                           uint64_t* loopsize, int* vertpl);
+/* the matrices outerbase owns (public/private fields, modandbase.h:61,113-119): which in
+ * {"basemat"(N x M),"basemat_gradhyp"(N x nge),"basescale"(N),"basescalemat"(N x d)};
+ * out may be NULL to query the shape. */
+int ob_outerbase_get_real(ob_outerbase* ob, const char* which, double* out, uint64_t* nrow, uint64_t* ncol);
 int ob_outerbase_getbase(ob_outerbase* ob, uint64_t dim_1based, double* out /* N x m_dim */);
 int ob_outerbase_getmat(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out /* N x K */);
 /* sq != 0 selects the squared operators (basematsq/basescalesq). */
@@ -148,6 +154,16 @@ int ob_outerbase_tmm_mat_dev(ob_outerbase* ob, int sq, const double* A_dev, uint
  * W = sum_k (nnz_k + 1), Lcols = distinct basis columns read, nodes = trie nodes. */
 int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uint64_t* nodes,
                              uint64_t* maxdepth);
+
+/* Host-side self check of the terms compiler (outerbase_b200/csrc/ob_terms.hpp): evaluates
+ * ONE row on the CPU by interpreting the compiled warp programs -- bcols holds that row's
+ * basemat (M values, knotptst layout).  out_phi_a = sum_k a_k prod_l B[t_kl] ;
+ * out_phit[k] = b * prod_l B[t_kl].  aug_dim = -1 for the plain program.  Test hook only:
+ * no product path calls it. */
+int ob_debug_terms_eval(const uint64_t* terms, uint64_t K, uint64_t d, const uint64_t* knotptst,
+                        int ngroups, int aug_dim, const double* bcols, const double* gcols0,
+                        const double* a, double b, double* out_phi_a, double* out_phit,
+                        uint64_t* stats /* W, Lcols, nodes, maxdepth, fast_ok, nslots, nwords_fwd, nwords_bwd */);
 
 /* ------------------------------------------------------------------ stateless linalg.h seam
  * Exactly the eight free functions of src/linalg.h:9-58 minus getmge_ (broken in

@@ -69,6 +69,7 @@ int orc_ctx_stream(orc_ctx*, void** s) { *s = nullptr; return ORC_OK; }
 int orc_comm_get_unique_id(void* id) { std::memset(id, 0, 128); return ORC_OK; }
 int orc_ctx_comm_init(orc_ctx*, int, int, const void*) { g_err = "oracle is single-rank"; return ORC_ERR_STATE; }
 int orc_ctx_comm_info(orc_ctx*, int* n, int* r) { *n = 1; *r = 0; return ORC_OK; }
+int orc_ctx_fp64_peak(orc_ctx*, double* t) { *t = 0; return ORC_OK; }
 int orc_ctx_launch_count(orc_ctx*, uint64_t* c) { *c = 0; return ORC_OK; }
 
 int orc_covf_numhyp(const char* name, uint64_t* n) { ORC_TRY *n = make_covf(name)->numhyp; ORC_CATCH }
@@ -192,6 +193,19 @@ int orc_outerbase_set_nthreads(orc_outerbase* ob, int n) { ob->ob->nthreads = n;
 int orc_outerbase_loopvals(orc_outerbase* ob, uint64_t* nthreads, uint64_t* chunksize, uint64_t* loopsize, int* vertpl) {
   *nthreads = ob->ob->nthreads; *chunksize = ob->ob->chunksize; *loopsize = ob->ob->loopsize; *vertpl = ob->ob->vertpl;
   return ORC_OK;
+}
+int orc_outerbase_get_real(orc_outerbase* ob, const char* which, double* out, uint64_t* nrow, uint64_t* ncol) {
+  ORC_TRY
+  const std::string w = which;
+  const outerbase& b = *ob->ob;
+  const std::vector<double>* src = nullptr;
+  if (w == "basemat") { src = &b.basemat.a; *nrow = b.basemat.nr; *ncol = b.basemat.nc; }
+  else if (w == "basemat_gradhyp") { src = &b.basemat_gradhyp.a; *nrow = b.basemat_gradhyp.nr; *ncol = b.basemat_gradhyp.nc; }
+  else if (w == "basescale") { src = &b.basescale; *nrow = b.basescale.size(); *ncol = 1; }
+  else if (w == "basescalemat") { src = &b.basescalemat.a; *nrow = b.basescalemat.nr; *ncol = b.basescalemat.nc; }
+  else throw std::invalid_argument("unknown matrix " + w);
+  if (out) std::copy(src->begin(), src->end(), out);
+  ORC_CATCH
 }
 int orc_outerbase_getbase(orc_outerbase* ob, uint64_t dim, double* out) {
   ORC_TRY

@@ -85,6 +85,11 @@ class Library:
         self.call("ctx_stream", self.ctx, C.byref(s))
         return s.value or 0
 
+    def fp64_peak(self) -> float:
+        v = C.c_double()
+        self.call("ctx_fp64_peak", self.ctx, C.byref(v))
+        return v.value
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         self.call("ctx_launch_count", self.ctx, C.byref(n))
@@ -122,6 +127,21 @@ class Library:
         out = np.empty((x1.size, x2.size, nh), order="F")
         self.call("covf_cov_gradhyp", self.ctx, name.encode(), _p(hyp), _p(x1), _u(x1.size), _p(x2), _u(x2.size), _p(out))
         return out
+
+    # -- host-side self check of the terms compiler (product only)
+    def debug_terms_eval(self, terms, knotptst, bcols, a, b=1.0, ngroups=16, aug_dim=-1, gcols0=None):
+        t = _terms(terms)
+        K, d = t.shape
+        kp = np.ascontiguousarray(knotptst, dtype=np.uint64)
+        bc, a = _f64(bcols), _f64(a)
+        g0 = _f64(gcols0) if gcols0 is not None else None
+        phia = C.c_double()
+        phit = np.empty(K)
+        stats = np.zeros(8, dtype=np.uint64)
+        self.call("debug_terms_eval", _p(t), _u(K), _u(d), _p(kp), C.c_int(ngroups), C.c_int(aug_dim), _p(bc), _p(g0),
+                  _p(a), C.c_double(b), C.byref(phia), _p(phit), _p(stats))
+        names = ("W", "Lcols", "nodes", "maxdepth", "fast_ok", "nslots", "nwords_fwd", "nwords_bwd")
+        return phia.value, phit, dict(zip(names, map(int, stats)))
 
     # -- object factories, named as in the Rcpp module
     def outermod(self):
@@ -337,6 +357,13 @@ class outerbase(_Handle):
     chunksize = property(lambda s: s._loopvals()[1])
     loopsize = property(lambda s: s._loopvals()[2])
     vertpl = property(lambda s: s._loopvals()[3])
+
+    def real(self, which):
+        r, c = C.c_uint64(), C.c_uint64()
+        self._lib.call("outerbase_get_real", self._h, which.encode(), C.c_void_p(0), C.byref(r), C.byref(c))
+        out = np.empty((r.value, c.value), order="F")
+        self._lib.call("outerbase_get_real", self._h, which.encode(), _p(out), C.byref(r), C.byref(c))
+        return out[:, 0].copy() if which == "basescale" else out
 
     def getbase(self, dim):
         kp = self._om.index("knotptst")

@@ -1,0 +1,168 @@
+/*
+ * ob_device.cuh -- device context, buffers and launcher declarations of the product.
+ * sm_100a only; there is NO CPU fallback: every entry point fails with OB_ERR_NOGPU
+ * when no CUDA device is present.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ob_model.hpp"
+#include "ob_terms.hpp"
+
+namespace obd {
+
+using u64 = uint64_t;
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NcclError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NoGpuError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define OB_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      throw obd::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+/* ---- NCCL, bound at run time so that the library loads without it and shares the
+ * libnccl.so.2 already mapped by the host process (e.g. torch's). */
+struct NcclUid { char b[128]; }; /* ncclUniqueId, passed BY VALUE to ncclCommInitRank */
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  static NcclApi& get();
+};
+
+struct Ctx {
+  int device = 0;
+  int sms = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  u64 launches = 0;
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  double* pinned = nullptr; /* small pinned scratch for scalar read-back */
+  explicit Ctx(int dev);
+  ~Ctx();
+  void sync() { OB_CUDA(cudaStreamSynchronize(stream)); }
+  void allreduce_sum(double* buf_dev, size_t n);
+};
+
+/* device buffer, grows on demand, never shrinks */
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  T* ensure(size_t n) {
+    if (n > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      OB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+      cap = n;
+    }
+    return p;
+  }
+  void upload(const T* h, size_t n, cudaStream_t s) {
+    ensure(n);
+    if (n) OB_CUDA(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+};
+
+constexpr int kTileRowsMax = 128;
+
+/* how one tile column is produced from what the bulk copies delivered */
+enum ColOp : int { COL_COPY = 0, COL_SQUARE = 1, COL_TWO_G_B = 2 };
+
+/* per (program, sq, hyper) pointer table: where each tile column is read from */
+struct ColTable {
+  DevBuf<const double*> load_src; /* ncol + naux base pointers (row 0 of the column) */
+  DevBuf<int> col_op;             /* ncol entries: op | (auxcol << 8) */
+  int ncol = 0, nload = 0;
+  bool has_ops = false;
+};
+
+/* compiled terms, resident on the device */
+struct DevProgram {
+  obt::Program host;
+  DevBuf<uint32_t> fwd, bwd, fwd_off, bwd_off, slot_base, slot_real, csr_ptr, csr_col;
+  DevBuf<int32_t> slot_term;
+  void upload(cudaStream_t s);
+};
+
+enum PhiMode : int { PHI_PLAIN = 0, PHI_UPDATE = 1, PHI_HESS = 2 };
+
+struct PhiAArgs {
+  const double* a = nullptr;       /* K coefficients (device) */
+  double* out = nullptr;           /* N: yhat (PLAIN/UPDATE) ; may be null for HESS */
+  double* w = nullptr;             /* N: UPDATE: -((yhat-y)/sd)/sd ; HESS: (yhat/sd)/sd */
+  const double* y = nullptr;       /* UPDATE */
+  double sd = 1.0;
+  double* ssq_partial = nullptr;   /* UPDATE: one partial per CTA (device, >= grid entries) */
+  int mode = PHI_PLAIN;
+};
+
+/* everything one Phi-type launch needs besides the vectors */
+struct PhiPlan {
+  const DevProgram* prog = nullptr;
+  const ColTable* cols = nullptr;
+  const double* scale = nullptr;   /* basescale (N) */
+  int sq = 0;                      /* use scale^2 */
+  u64 N = 0;
+};
+
+struct Workspace {
+  DevBuf<double> partial;  /* Phi^T: grid x nslots partial sums */
+  DevBuf<double> ssq;      /* per-CTA residual sums of squares */
+};
+
+int phi_grid(const Ctx& c, u64 N, int tile_rows);
+/* Phi a (trie/Horner kernel, or the brute-force kernel when the program is not fast_ok) */
+void launch_phi_a(Ctx& c, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
+/* Phi^T w -> out (K, device); result is the LOCAL (this rank's rows) sum */
+void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
+/* explicit Phi (N x K column-major, device), getm_ linalg.cpp:685-715 */
+void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo);
+/* sum of n per-CTA partials, fixed order -> out[0] */
+void launch_sum_partials(Ctx& c, const double* partial, int n, double* out);
+
+/* basis build: cov(x, knots) . rotmat, normalise (modandbase.cpp:285-327, 547-626) */
+struct BuildDims {
+  int kind; int m; int nh;
+  double hyp[2];
+  u64 knot_off;  /* offset of this dim's knots in the transformed-knot arrays */
+  u64 col_off;   /* knotptst[l] */
+  u64 ge_off[2]; /* gest[h] for the dim's hypers */
+  u64 rot_off;   /* column offset of the dim's block in rotmat */
+  u64 rotg_off[2];
+};
+void launch_basis_build(Ctx& c, const std::vector<BuildDims>& dims, const double* x_dev, u64 N, u64 ld,
+                        const double* knots_dev, const double* rot_dev, u64 rot_ld, const double* rotg_dev,
+                        double* basemat, double* basematge, double* scalemat, double* scale, bool dograd);
+void launch_getbase(Ctx& c, const double* basemat, const double* scalemat_col, u64 N, u64 ld, u64 col0, u64 m, double* out);
+void launch_cov(Ctx& c, int kind, const double* hyp, const double* x1, u64 n1, const double* x2, u64 n2,
+                double* out, double* outg /* may be null */);
+/* FP64 FMA peak of this GPU in TFLOP/s (micro-benchmark, ~50 ms) */
+double measure_fp64_peak(Ctx& c);
+/* elementwise helpers */
+void launch_fill(Ctx& c, double* p, u64 n, double v);
+/* outge[:,h] (N) dotted with w (N) -> out[h], deterministic two-stage */
+void launch_dot_partials(Ctx& c, const double* a, const double* b, u64 n, double* partial, int* nblocks);
+
+} // namespace obd

@@ -1,0 +1,755 @@
+/*
+ * ob_engine.hpp -- the reference's C++ classes re-hosted on the GPU kernels.
+ *
+ *   OuterBase    class outerbase   src/modandbase.h:57-125, src/modandbase.cpp:459-922
+ *   Lpdf         class lpdf        src/fit.h:23-90,   optcg src/fit.cpp:37-96
+ *   LogprGauss   logpr_gauss       src/lpdfs/logpr_gauss.cpp:41-145   (K-length, host)
+ *   LoglikGauss  loglik_gauss      src/lpdfs/loglik_gauss.cpp:41-179  (N-length work on the GPU)
+ *   LpdfVec      lpdfvec           src/fit.cpp:174-267,310-428,557-607 (diagonal branch)
+ *   PredGauss    pred_gauss        src/lpdfs/loglik_gauss.cpp:196-227
+ *
+ * State that is N-sized (x, basemat, basemat_gradhyp, basescale, y, yhat, residuals)
+ * lives in HBM for the lifetime of the object; K- and H-sized state is mirrored on the
+ * host, where the reference's K-vector algebra (CG scalars, prior, marginal
+ * adjustment) is executed in the reference's own summation order.
+ * basematsq / basescalesq / basematsq_gradhyp are never stored: the kernels square the
+ * staged tile in shared memory (halves the HBM footprint of modandbase.cpp:527-531).
+ */
+#pragma once
+#include <cstring>
+#include <list>
+
+#include "ob_device.cuh"
+
+namespace obe {
+
+using obd::Ctx;
+using obd::DevBuf;
+using obh::OuterMod;
+using u64 = uint64_t;
+
+inline u64 pad128(u64 n) { return ((n + 127) / 128) * 128; }
+
+inline bool all_finite(const std::vector<double>& v) {
+  for (double x : v) if (!std::isfinite(x)) return false;
+  return true;
+}
+
+/* ------------------------------------------------------------------ outerbase */
+struct OuterBase {
+  Ctx& ctx;
+  const OuterMod* om;
+  u64 N = 0, ld = 0, d = 0, H = 0, M = 0, Mge = 0;
+  bool dograd = true;
+  u64 nthreads = 1;
+  u64 om_version = 0;
+  std::vector<u64> knotptst, gest, hypmatch, hypst;
+  DevBuf<double> x, basemat, basematge, scalemat, scale;
+  DevBuf<double> knots_dev, rot_dev, rotg_dev;
+  obd::Workspace ws;
+  DevBuf<double> tmpK, tmpN, tmpN2, tmpP;
+
+  struct ProgEntry { std::vector<u64> terms; u64 K; int aug; std::unique_ptr<obd::DevProgram> prog; };
+  std::list<ProgEntry> programs;
+  struct ColEntry { const obd::DevProgram* prog; int sq; int h; std::unique_ptr<obd::ColTable> ct; };
+  std::list<ColEntry> coltables;
+  /* terms installed by set_terms for the *_dev entry points */
+  std::vector<u64> cur_terms;
+  u64 cur_K = 0;
+
+  OuterBase(Ctx& c, const OuterMod* om_, const double* xh, u64 N_, bool dograd_) : ctx(c), om(om_), N(N_), dograd(dograd_) {
+    if (!om->knots_set) throw std::range_error("Need to set covfs and knots before building.");
+    d = om->d;
+    ld = pad128(N);
+    nthreads = 1;
+    /* x is copied (modandbase.h:60), column by column into the padded layout */
+    x.ensure(ld * d);
+    OB_CUDA(cudaMemsetAsync(x.p, 0, ld * d * sizeof(double), ctx.stream));
+    for (u64 l = 0; l < d; ++l)
+      if (N) OB_CUDA(cudaMemcpyAsync(x.p + l * ld, xh + l * N, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
+    build();
+  }
+
+  /* stateless linalg.h seam (src/linalg.h:9-58): wrap caller-provided basemat / basescale
+   * (and optionally basematge) instead of building them; om stays null. */
+  OuterBase(Ctx& c, u64 N_, u64 d_, u64 M_, const u64* kp, const double* bm, const double* bs,
+            const double* bmge, u64 Mge_, const u64* ge, const u64* hm, u64 H_)
+      : ctx(c), om(nullptr), N(N_), dograd(bmge != nullptr) {
+    d = d_; M = M_; Mge = Mge_; H = H_;
+    ld = pad128(N);
+    knotptst.assign(kp, kp + d + 1);
+    if (knotptst[d] > M) throw std::range_error("knotptst exceeds the columns of basemat");
+    if (bmge) { gest.assign(ge, ge + H + 1); hypmatch.assign(hm, hm + H); }
+    auto put = [&](DevBuf<double>& dst, const double* src, u64 ncol) {
+      dst.ensure(ld * std::max<u64>(ncol, 1));
+      OB_CUDA(cudaMemsetAsync(dst.p, 0, ld * std::max<u64>(ncol, 1) * sizeof(double), ctx.stream));
+      for (u64 j = 0; j < ncol; ++j)
+        if (N) OB_CUDA(cudaMemcpyAsync(dst.p + j * ld, src + j * N, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    };
+    put(basemat, bm, M);
+    put(scale, bs, 1);
+    if (bmge) put(basematge, bmge, Mge);
+    ctx.sync();
+  }
+
+  void check_terms(const u64* terms, u64 K) const {
+    for (u64 l = 0; l < d; ++l) {
+      const u64 m = knotptst[l + 1] - knotptst[l];
+      for (u64 k = 0; k < K; ++k)
+        if (terms[k + l * K] >= m) throw std::range_error("terms level exceeds the number of knots");
+    }
+  }
+
+  /* outerbase::build (modandbase.cpp:547-626): re-reads the CURRENT state of om */
+  void build() {
+    if (!om) throw std::logic_error("this outerbase wraps caller-provided matrices");
+    d = om->d; hypmatch = om->hypmatch; hypst = om->hypst; gest = om->gest; knotptst = om->knotptst; /* setvals_ :492 */
+    H = hypmatch.size();
+    M = om->nknot();
+    Mge = om->nge();
+    basemat.ensure(ld * M);
+    if (dograd) basematge.ensure(ld * Mge);
+    scalemat.ensure(ld * d);
+    scale.ensure(ld);
+    knots_dev.upload(om->knotpt, ctx.stream);
+    rot_dev.upload(om->rotmat.a, ctx.stream);
+    if (dograd) rotg_dev.upload(om->rotmat_gradhyp.a, ctx.stream);
+    std::vector<obd::BuildDims> dims(d);
+    for (u64 l = 0; l < d; ++l) {
+      obd::BuildDims& D = dims[l];
+      D.kind = om->cov[l].kind; D.m = (int)om->mdim(l); D.nh = om->cov[l].numhyp;
+      D.hyp[0] = om->hyp[hypst[l]]; D.hyp[1] = D.nh > 1 ? om->hyp[hypst[l] + 1] : 0.0;
+      D.knot_off = knotptst[l]; D.col_off = knotptst[l]; D.rot_off = knotptst[l];
+      for (int h = 0; h < D.nh; ++h) { D.ge_off[h] = gest[hypst[l] + h]; D.rotg_off[h] = gest[hypst[l] + h]; }
+    }
+    obd::launch_basis_build(ctx, dims, x.p, N, ld, knots_dev.p, rot_dev.p, om->rotmat.nr, rotg_dev.p, basemat.p,
+                            dograd ? basematge.p : nullptr, scalemat.p, scale.p, dograd);
+    ctx.sync(); /* host vectors above must outlive the async uploads */
+    coltables.clear(); /* buffers may have moved */
+    om_version = om->version;
+  }
+
+  obd::DevProgram* program(const u64* terms, u64 K, int aug) {
+    for (auto it = programs.begin(); it != programs.end(); ++it)
+      if (it->K == K && it->aug == aug && std::memcmp(it->terms.data(), terms, K * d * sizeof(u64)) == 0) {
+        programs.splice(programs.begin(), programs, it);
+        return programs.front().prog.get();
+      }
+    check_terms(terms, K);
+    ProgEntry e;
+    e.terms.assign(terms, terms + K * d);
+    e.K = K; e.aug = aug;
+    e.prog.reset(new obd::DevProgram());
+    e.prog->host = obt::compile(terms, K, d, 16, aug);
+    e.prog->upload(ctx.stream);
+    ctx.sync();
+    programs.push_front(std::move(e));
+    while (programs.size() > 96) {
+      const obd::DevProgram* dead = programs.back().prog.get();
+      coltables.remove_if([&](const ColEntry& c) { return c.prog == dead; });
+      programs.pop_back();
+    }
+    return programs.front().prog.get();
+  }
+
+  obd::ColTable* coltable(const obd::DevProgram* prog, int sq, int h) {
+    for (auto& c : coltables) if (c.prog == prog && c.sq == sq && c.h == h) return c.ct.get();
+    const obt::Program& P = prog->host;
+    std::vector<const double*> src;
+    std::vector<int> ops;
+    std::vector<const double*> aux;
+    for (const obt::ColRef& cr : P.cols) {
+      if (!cr.aug) {
+        src.push_back(basemat.p + (knotptst[cr.dim] + cr.level) * ld);
+        ops.push_back(sq ? obd::COL_SQUARE : obd::COL_COPY);
+      } else {
+        if (h < 0 || hypmatch[h] != cr.dim || !dograd) throw std::logic_error("gradient column without a hyper-parameter");
+        src.push_back(basematge.p + (gest[h] + cr.level) * ld);
+        if (sq) { /* basematsq_gradhyp = 2*(Rt % R), modandbase.cpp:588-590 */
+          ops.push_back(obd::COL_TWO_G_B | (int)((P.cols.size() + aux.size()) << 8));
+          aux.push_back(basemat.p + (knotptst[cr.dim] + cr.level) * ld);
+        } else ops.push_back(obd::COL_COPY);
+      }
+    }
+    ColEntry e;
+    e.prog = prog; e.sq = sq; e.h = h;
+    e.ct.reset(new obd::ColTable());
+    e.ct->ncol = (int)src.size();
+    src.insert(src.end(), aux.begin(), aux.end());
+    e.ct->nload = (int)src.size();
+    e.ct->has_ops = sq != 0;
+    e.ct->load_src.upload(src, ctx.stream);
+    e.ct->col_op.upload(ops, ctx.stream);
+    ctx.sync();
+    coltables.push_front(std::move(e));
+    return coltables.front().ct.get();
+  }
+
+  obd::PhiPlan plan(const obd::DevProgram* prog, int sq, int h) {
+    obd::PhiPlan pl;
+    pl.prog = prog; pl.cols = coltable(prog, sq, h); pl.scale = scale.p; pl.sq = sq; pl.N = N;
+    return pl;
+  }
+
+  /* ---- device-pointer operations (stream ordered, not synchronised) */
+  void mm_dev(const u64* terms, u64 K, int sq, const double* a_dev, double* out_dev) {
+    obd::PhiAArgs a; a.a = a_dev; a.out = out_dev; a.mode = obd::PHI_PLAIN;
+    obd::launch_phi_a(ctx, plan(program(terms, K, -1), sq, -1), a, ws, nullptr);
+  }
+  void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true) {
+    obd::launch_phi_t(ctx, plan(program(terms, K, -1), sq, -1), w_dev, out_dev, ws);
+    if (reduce_ranks) ctx.allreduce_sum(out_dev, K);
+  }
+  /* prodmmge_: outge column h = augmented-program product (ob_terms.hpp) */
+  void mm_ge_dev(const u64* terms, u64 K, int sq, const double* a_dev, double* out_dev, double* outge_dev, u64 ldo) {
+    if (!dograd) throw std::logic_error("outerbase was built without gradients");
+    if (out_dev) mm_dev(terms, K, sq, a_dev, out_dev);
+    for (u64 h = 0; h < H; ++h) {
+      obd::PhiAArgs a; a.a = a_dev; a.out = outge_dev + h * ldo; a.mode = obd::PHI_PLAIN;
+      obd::launch_phi_a(ctx, plan(program(terms, K, (int)hypmatch[h]), sq, (int)h), a, ws, nullptr);
+    }
+  }
+  void tmm_ge_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev /* K*(1+H): out | outge */) {
+    if (!dograd) throw std::logic_error("outerbase was built without gradients");
+    obd::launch_phi_t(ctx, plan(program(terms, K, -1), sq, -1), w_dev, out_dev, ws);
+    for (u64 h = 0; h < H; ++h)
+      obd::launch_phi_t(ctx, plan(program(terms, K, (int)hypmatch[h]), sq, (int)h), w_dev, out_dev + (1 + h) * K, ws);
+    ctx.allreduce_sum(out_dev, K * (1 + H));
+  }
+
+  /* ---- host-pointer operations (the reference's call signatures) */
+  void d2h(double* dst, const double* src, u64 n) {
+    if (n) OB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+  }
+  void mm(int sq, const u64* terms, u64 K, const double* a, double* out) {
+    tmpK.upload(a, K, ctx.stream);
+    tmpN.ensure(ld);
+    mm_dev(terms, K, sq, tmpK.p, tmpN.p);
+    d2h(out, tmpN.p, N);
+  }
+  void tmm(int sq, const u64* terms, u64 K, const double* a, double* out) {
+    tmpN.ensure(ld);
+    if (N) OB_CUDA(cudaMemcpyAsync(tmpN.p, a, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    tmpK.ensure(K);
+    tmm_dev(terms, K, sq, tmpN.p, tmpK.p);
+    d2h(out, tmpK.p, K);
+  }
+  void mm_gradhyp(int sq, const u64* terms, u64 K, const double* a, double* out, double* outge) {
+    tmpK.upload(a, K, ctx.stream);
+    tmpN.ensure(ld);
+    tmpN2.ensure(ld * std::max<u64>(H, 1));
+    mm_ge_dev(terms, K, sq, tmpK.p, out ? tmpN.p : nullptr, tmpN2.p, ld);
+    if (out) d2h(out, tmpN.p, N);
+    for (u64 h = 0; h < H; ++h) d2h(outge + h * N, tmpN2.p + h * ld, N);
+  }
+  void tmm_gradhyp(int sq, const u64* terms, u64 K, const double* a, double* out, double* outge) {
+    tmpN.ensure(ld);
+    if (N) OB_CUDA(cudaMemcpyAsync(tmpN.p, a, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    tmpK.ensure(K * (1 + H));
+    tmm_ge_dev(terms, K, sq, tmpN.p, tmpK.p);
+    std::vector<double> h(K * (1 + H));
+    d2h(h.data(), tmpK.p, K * (1 + H));
+    if (out) std::copy(h.begin(), h.begin() + K, out);
+    std::copy(h.begin() + K, h.end(), outge);
+  }
+  /* multi right-hand sides: one pass per column for now (DMMA kernel: DESIGN.md "next") */
+  void mm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 C, double* out_dev, u64 ldo) {
+    for (u64 c = 0; c < C; ++c) mm_dev(terms, K, sq, A_dev + c * K, out_dev + c * ldo);
+  }
+  void tmm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 lda, u64 C, double* out_dev) {
+    for (u64 c = 0; c < C; ++c) tmm_dev(terms, K, sq, A_dev + c * lda, out_dev + c * K, false);
+    ctx.allreduce_sum(out_dev, K * C);
+  }
+  void mm_mat(int sq, const u64* terms, u64 K, const double* A, u64 C, double* out) {
+    tmpK.upload(A, K * C, ctx.stream);
+    tmpN2.ensure(ld * C);
+    mm_mat_dev(terms, K, sq, tmpK.p, C, tmpN2.p, ld);
+    for (u64 c = 0; c < C; ++c) d2h(out + c * N, tmpN2.p + c * ld, N);
+  }
+  void tmm_mat(int sq, const u64* terms, u64 K, const double* A, u64 C, double* out) {
+    tmpN2.ensure(ld * C);
+    for (u64 c = 0; c < C; ++c)
+      if (N) OB_CUDA(cudaMemcpyAsync(tmpN2.p + c * ld, A + c * N, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    tmpK.ensure(K * C);
+    tmm_mat_dev(terms, K, sq, tmpN2.p, ld, C, tmpK.p);
+    d2h(out, tmpK.p, K * C);
+  }
+  void getmat(const u64* terms, u64 K, double* out) {
+    obd::DevProgram* pr = program(terms, K, -1);
+    tmpP.ensure(ld * K);
+    obd::launch_getmat(ctx, plan(pr, 0, -1), tmpP.p, ld);
+    for (u64 k = 0; k < K; ++k) d2h(out + k * N, tmpP.p + k * ld, N);
+  }
+  void getbase(u64 dim1, double* out) {
+    if (dim1 < 1 || dim1 > d) throw std::range_error("dim out of range");
+    const u64 l = dim1 - 1, m = knotptst[l + 1] - knotptst[l];
+    tmpP.ensure(N * m + 1);
+    obd::launch_getbase(ctx, basemat.p, scalemat.p + l * ld, N, ld, knotptst[l], m, tmpP.p);
+    d2h(out, tmpP.p, N * m);
+  }
+};
+
+/* ------------------------------------------------------------------ lpdf family */
+struct Lpdf {
+  double val = 0;
+  std::vector<double> grad, gradhyp, gradpara, para, coeff, totdiaghess, para0, paravar;
+  std::vector<u64> terms; /* K x d */
+  u64 d = 0;
+  bool didfulltothess = false, didnotothess = true;
+  bool compute_val = true, compute_grad = true, compute_gradhyp = false, compute_gradpara = false;
+  u64 npara = 0, nterms = 0, cg_iters = 0;
+  virtual ~Lpdf() {}
+  virtual void setnthreads(int) {}
+  virtual double paralpdf(const double* p, u64 n) const { /* fit.cpp:133-142 */
+    if (npara != n) return -std::numeric_limits<double>::infinity();
+    std::vector<double> t(n);
+    for (u64 l = 0; l < n; ++l) { const double e = p[l] - para0[l]; t[l] = e * e / paravar[l]; }
+    return 0.0 - 0.5 * obh::sum2(t.data(), n);
+  }
+  virtual void paralpdf_grad(const double* p, u64 n, double* out) const { /* fit.cpp:146-157 */
+    for (u64 l = 0; l < para.size(); ++l) out[l] = 0.0;
+    if (npara != n) return;
+    for (u64 l = 0; l < n; ++l) out[l] -= (p[l] - para0[l]) / paravar[l];
+  }
+  virtual void updateom() {}
+  virtual void updatepara(const double*, u64) {}
+  virtual void updateterms(const u64*, u64) {}
+  virtual void update(const std::vector<double>&) {}
+  virtual std::vector<double> hessmult(const std::vector<double>&) { return {}; }
+  virtual std::vector<double> diaghess() { return {}; }
+  virtual std::vector<double> diaghessgradhyp() { return {}; } /* K x H */
+  virtual std::vector<double> diaghessgradpara() { return {}; } /* K x npara */
+  virtual void settotdiaghess(const std::vector<double>& dh) { totdiaghess = dh; didfulltothess = false; didnotothess = false; }
+  virtual u64 nhyp() const { return 0; }
+  virtual u64 nrow() const { return 0; }
+
+  /* lpdf::optcg, fit.cpp:37-96.  The K-length algebra runs on the host in the
+   * reference's order (Armadillo's two-accumulator accu); update/hessmult are the GPU. */
+  virtual void optcg(double tol, u64 maxepch) {
+    compute_val = true; compute_grad = true; compute_gradhyp = false; compute_gradpara = false;
+    if (coeff.size() != nterms) coeff.assign(nterms, 0.0);
+    update(std::vector<double>(coeff));
+    std::vector<double> m = diaghess();
+    cg_iters = 0;
+    if (!all_finite(m) && !all_finite(grad)) { val = -std::numeric_limits<double>::infinity(); return; }
+    const u64 K = nterms;
+    std::vector<double> rm(K), t(K);
+    for (u64 i = 0; i < K; ++i) rm[i] = grad[i] / m[i];
+    std::vector<double> p = rm;
+    std::vector<double> q = hessmult(p);
+    double num = 0, beta = 0, denom = 1, alpha = 0, num2 = 0, valo = val, valdiff = 10;
+    u64 k;
+    for (k = 0; k < maxepch; k++) {
+      for (u64 i = 0; i < K; ++i) t[i] = grad[i] * rm[i];
+      num = obh::sum2(t.data(), K);
+      if (num < tol && valdiff < tol) break;
+      for (u64 i = 0; i < K; ++i) t[i] = q[i] * p[i];
+      denom = obh::sum2(t.data(), K);
+      alpha = num / denom;
+      for (u64 i = 0; i < K; ++i) coeff[i] += alpha * p[i];
+      valo = val;
+      update(std::vector<double>(coeff));
+      valdiff = val - valo;
+      for (u64 i = 0; i < K; ++i) rm[i] = grad[i] / m[i];
+      for (u64 i = 0; i < K; ++i) t[i] = (alpha * q[i]) * rm[i];
+      num2 = -obh::sum2(t.data(), K);
+      beta = num2 / num;
+      for (u64 i = 0; i < K; ++i) p[i] = rm[i] + beta * p[i];
+      q = hessmult(p);
+    }
+    cg_iters = k;
+    compute_gradhyp = true; compute_gradpara = true;
+    update(std::vector<double>(coeff));
+    compute_gradhyp = false; compute_gradpara = false;
+  }
+};
+
+struct LogprGauss : Lpdf { /* logpr_gauss.cpp:41-145 */
+  const OuterMod* om;
+  std::vector<double> coeffsd, coefflvarge, stdresid;
+  double sca = 1;
+  LogprGauss(const OuterMod* om_, const u64* t, u64 K) : om(om_) {
+    d = om->d; npara = 1;
+    terms.assign(t, t + K * d);
+    para0 = {6}; paravar = {4};
+    nterms = K;
+    para = para0;
+    sca = std::exp(para[0]);
+    updateom();
+  }
+  void updateom() override {
+    coeffsd.resize(nterms);
+    om->getvar(terms.data(), nterms, coeffsd.data());
+    for (double& v : coeffsd) v = std::sqrt(v);
+    coefflvarge.resize(nterms * om->nhyp());
+    om->getlvar_gradhyp(terms.data(), nterms, coefflvarge.data());
+  }
+  void updatepara(const double* p, u64 n) override { para.assign(p, p + n); sca = std::exp(para[0]); }
+  void updateterms(const u64* t, u64 K) override { terms.assign(t, t + K * d); nterms = K; updateom(); }
+  void update(const std::vector<double>& c) override {
+    coeff = c;
+    const u64 K = coeff.size(), H = om->nhyp();
+    stdresid.resize(K);
+    for (u64 i = 0; i < K; ++i) stdresid[i] = coeff[i] / (coeffsd[i] * sca);
+    std::vector<double> t(K), t2(K);
+    if (compute_val) {
+      for (u64 i = 0; i < K; ++i) { t[i] = stdresid[i] * stdresid[i]; t2[i] = std::log(coeffsd[i] * sca); }
+      val = -0.5 * obh::sum2(t.data(), K) - obh::sum2(t2.data(), K);
+    }
+    if (compute_gradhyp) {
+      gradhyp.assign(H, 0.0);
+      for (u64 i = 0; i < K; ++i) t[i] = stdresid[i] * stdresid[i] - 1;
+      for (u64 h = 0; h < H; ++h) {
+        double s1 = 0, s2 = 0;
+        u64 j;
+        const double* g = coefflvarge.data() + h * K;
+        for (j = 1; j < K; j += 2) { s1 += (0.5 * g[j - 1]) * t[j - 1]; s2 += (0.5 * g[j]) * t[j]; }
+        if ((j - 1) < K) s1 += (0.5 * g[j - 1]) * t[j - 1];
+        gradhyp[h] = s1 + s2;
+      }
+    }
+    if (compute_gradpara) {
+      for (u64 i = 0; i < K; ++i) t[i] = stdresid[i] * stdresid[i];
+      gradpara = {obh::sum2(t.data(), K) - double(coeffsd.size())};
+    }
+    if (compute_grad) {
+      grad.resize(K);
+      for (u64 i = 0; i < K; ++i) grad[i] = -1. * stdresid[i] / (coeffsd[i] * sca);
+    }
+  }
+  std::vector<double> hessmult(const std::vector<double>& g) override {
+    std::vector<double> o(g.size());
+    for (u64 i = 0; i < g.size(); ++i) { const double s = coeffsd[i] * sca; o[i] = g[i] / (s * s); }
+    return o;
+  }
+  std::vector<double> diaghess() override {
+    std::vector<double> o(coeffsd.size());
+    for (u64 i = 0; i < o.size(); ++i) { const double s = coeffsd[i] * sca; o[i] = 1. / (s * s); }
+    return o;
+  }
+  std::vector<double> diaghessgradhyp() override {
+    std::vector<double> o = coefflvarge;
+    const u64 K = nterms, H = om->nhyp();
+    for (u64 h = 0; h < H; ++h) for (u64 i = 0; i < K; ++i) { const double s = coeffsd[i] * sca; o[i + h * K] = -(o[i + h * K] / (s * s)); }
+    return o;
+  }
+  std::vector<double> diaghessgradpara() override {
+    std::vector<double> o(nterms);
+    for (u64 i = 0; i < nterms; ++i) { const double s = coeffsd[i] * sca; o[i] = -2. / (s * s); }
+    return o;
+  }
+  u64 nhyp() const override { return om->nhyp(); }
+};
+
+struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
+  Ctx& ctx;
+  const OuterMod* om;
+  OuterBase ob;
+  std::vector<double> x_host; /* kept for predictor(loglik), loglik_gauss.cpp:198 */
+  u64 N = 0;
+  double Nglobal = 0;
+  double obssd = 1;
+  DevBuf<double> y, yhat, w, kbuf, red, gebuf, ones;
+  std::vector<double> yhat_host;
+  bool yhat_valid = false;
+
+  LoglikGauss(Ctx& c, const OuterMod* om_, const u64* t, u64 K, const double* yh, const double* xh, u64 N_)
+      : ctx(c), om(om_), ob(c, om_, xh, N_, true), N(N_) {
+    d = om->d; npara = 1;
+    terms.assign(t, t + K * d);
+    nterms = K;
+    x_host.assign(xh, xh + N * d);
+    y.ensure(ob.ld);
+    OB_CUDA(cudaMemsetAsync(y.p, 0, ob.ld * sizeof(double), ctx.stream));
+    if (N) OB_CUDA(cudaMemcpyAsync(y.p, yh, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    yhat.ensure(ob.ld); w.ensure(ob.ld);
+    ctx.sync();
+    /* para0 = log(0.01*var(y)), loglik_gauss.cpp:48 (Armadillo two-pass var); over ALL ranks' rows */
+    double stats[3] = {double(N), 0, 0};
+    for (u64 i = 0; i < N; ++i) stats[1] += yh[i];
+    if (ctx.nranks > 1) { allreduce_host(stats, 2); }
+    Nglobal = stats[0];
+    double var;
+    if (ctx.nranks > 1) {
+      const double mean = stats[1] / stats[0];
+      double ss[1] = {0};
+      for (u64 i = 0; i < N; ++i) ss[0] += (yh[i] - mean) * (yh[i] - mean);
+      allreduce_host(ss, 1);
+      var = ss[0] / (Nglobal - 1);
+    } else var = arma_var(yh, N);
+    para0 = {std::log(0.01 * var)};
+    paravar = {1};
+    para = para0;
+    obssd = std::exp(para[0]);
+  }
+  void allreduce_host(double* v, u64 n) {
+    red.upload(v, n, ctx.stream);
+    ctx.allreduce_sum(red.p, n);
+    OB_CUDA(cudaMemcpyAsync(v, red.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+  }
+  static double arma_var(const double* x, u64 n) {
+    if (n < 2) return 0.0;
+    const double mean = obh::sum2(x, n) / double(n);
+    double a2 = 0, a3 = 0;
+    u64 i, j;
+    for (i = 0, j = 1; j < n; i += 2, j += 2) { const double ti = mean - x[i], tj = mean - x[j]; a2 += ti * ti + tj * tj; a3 += ti + tj; }
+    if (i < n) { const double ti = mean - x[i]; a2 += ti * ti; a3 += ti; }
+    return (a2 - a3 * a3 / double(n)) / double(n - 1);
+  }
+  void setnthreads(int k) override { ob.nthreads = k; }
+  void updateom() override { ob.build(); }
+  void updatepara(const double* p, u64 n) override { para.assign(p, p + n); obssd = std::exp(para[0]); }
+  void updateterms(const u64* t, u64 K) override { terms.assign(t, t + K * d); nterms = K; }
+
+  void update(const std::vector<double>& c) override { /* loglik_gauss.cpp:110-130 */
+    coeff = c;
+    const u64 K = nterms, H = ob.H;
+    if (c.size() != K) throw std::range_error("coeff must have one entry per term");
+    kbuf.upload(coeff, ctx.stream);
+    obd::DevProgram* pr = ob.program(terms.data(), K, -1);
+    obd::PhiAArgs a;
+    a.a = kbuf.p; a.out = yhat.p; a.w = w.p; a.y = y.p; a.sd = obssd; a.mode = obd::PHI_UPDATE;
+    int grid = 0;
+    obd::launch_phi_a(ctx, ob.plan(pr, 0, -1), a, ob.ws, &grid);
+    yhat_valid = false;
+    /* reduction buffer: [grad (K) | ssq | gradhyp (H)] -> one allreduce */
+    red.ensure(K + 1 + H);
+    OB_CUDA(cudaMemsetAsync(red.p, 0, (K + 1 + H) * sizeof(double), ctx.stream));
+    if (grid > 0) obd::launch_sum_partials(ctx, ob.ws.ssq.p, grid, red.p + K);
+    const bool dohyp = compute_grad && compute_gradhyp;
+    if (compute_grad) obd::launch_phi_t(ctx, ob.plan(pr, 0, -1), w.p, red.p, ob.ws);
+    if (dohyp) { /* gradhyp = residtemp^T * yhatge, :127 -- yhatge column h is never stored */
+      gebuf.ensure(ob.ld + 4 * ctx.sms);
+      for (u64 h = 0; h < H; ++h) {
+        obd::PhiAArgs g; g.a = kbuf.p; g.out = gebuf.p; g.mode = obd::PHI_PLAIN;
+        obd::launch_phi_a(ctx, ob.plan(ob.program(terms.data(), K, (int)ob.hypmatch[h]), 0, (int)h), g, ob.ws, nullptr);
+        int nb = 0;
+        obd::launch_dot_partials(ctx, w.p, gebuf.p, N, gebuf.p + ob.ld, &nb);
+        obd::launch_sum_partials(ctx, gebuf.p + ob.ld, nb, red.p + K + 1 + h);
+      }
+    }
+    ctx.allreduce_sum(red.p, K + 1 + H);
+    std::vector<double> r(K + 1 + H);
+    ob.d2h(r.data(), red.p, K + 1 + H);
+    const double ssq = r[K];
+    if (compute_val) val = -0.5 * ssq - Nglobal * std::log(obssd);
+    if (compute_grad) {
+      grad.assign(r.begin(), r.begin() + K);
+      if (compute_gradhyp) gradhyp.assign(r.begin() + K + 1, r.end());
+      if (compute_gradpara) gradpara = {ssq - Nglobal};
+    }
+  }
+  std::vector<double> hessmult(const std::vector<double>& g) override { /* :137-145 */
+    const u64 K = nterms;
+    kbuf.upload(g, ctx.stream);
+    obd::DevProgram* pr = ob.program(terms.data(), K, -1);
+    obd::PhiAArgs a;
+    a.a = kbuf.p; a.w = w.p; a.sd = obssd; a.mode = obd::PHI_HESS;
+    obd::launch_phi_a(ctx, ob.plan(pr, 0, -1), a, ob.ws, nullptr);
+    red.ensure(K);
+    obd::launch_phi_t(ctx, ob.plan(pr, 0, -1), w.p, red.p, ob.ws);
+    ctx.allreduce_sum(red.p, K);
+    std::vector<double> o(K);
+    ob.d2h(o.data(), red.p, K);
+    return o;
+  }
+  const double* ones_dev() {
+    if (ones.cap < ob.ld) { ones.ensure(ob.ld); obd::launch_fill(ctx, ones.p, ob.ld, 1.0); }
+    return ones.p;
+  }
+  std::vector<double> sqcolsums() { /* modandbase.cpp:863-867 */
+    const u64 K = nterms;
+    red.ensure(K);
+    ob.tmm_dev(terms.data(), K, 1, ones_dev(), red.p);
+    std::vector<double> o(K);
+    ob.d2h(o.data(), red.p, K);
+    return o;
+  }
+  std::vector<double> diaghess() override { /* :154-157 */
+    std::vector<double> lh = sqcolsums();
+    const double c = std::exp(-2 * para[0]);
+    for (double& v : lh) v = c * v;
+    return lh;
+  }
+  std::vector<double> diaghessgradhyp() override { /* :165-168 */
+    const u64 K = nterms, H = ob.H;
+    red.ensure(K * (1 + H));
+    ob.tmm_ge_dev(terms.data(), K, 1, ones_dev(), red.p);
+    std::vector<double> all(K * (1 + H));
+    ob.d2h(all.data(), red.p, K * (1 + H));
+    std::vector<double> o(all.begin() + K, all.end());
+    const double c = std::exp(-2 * para[0]);
+    for (double& v : o) v = c * v;
+    return o;
+  }
+  std::vector<double> diaghessgradpara() override { /* :176-179 */
+    std::vector<double> lh = sqcolsums();
+    const double c = -2 * std::exp(-2 * para[0]);
+    for (double& v : lh) v = c * v;
+    return lh;
+  }
+  const std::vector<double>& get_yhat() {
+    if (!yhat_valid) { yhat_host.resize(N); ob.d2h(yhat_host.data(), yhat.p, N); yhat_valid = true; }
+    return yhat_host;
+  }
+  u64 nhyp() const override { return ob.H; }
+  u64 nrow() const override { return N; }
+};
+
+struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
+  double val_margadj = 0;
+  std::vector<double> gradhyp_margadj, gradpara_margadj;
+  bool domargadj = true;
+  std::vector<double> diaghessv, diaghessgradhypv, diaghessgradparav;
+  bool redohess = true;
+  Lpdf* kid[2];
+  u64 parasrt[2], paraend[2];
+  LpdfVec(Lpdf* a, Lpdf* b) {
+    kid[0] = a; kid[1] = b;
+    terms = a->terms; d = a->d;
+    nterms = a->nterms;
+    parasrt[0] = 0; paraend[0] = a->npara - 1;
+    parasrt[1] = paraend[0] + 1; paraend[1] = parasrt[1] + b->npara - 1;
+    para.assign(1 + paraend[1], 0.0);
+    std::copy(a->para.begin(), a->para.end(), para.begin() + parasrt[0]);
+    std::copy(b->para.begin(), b->para.end(), para.begin() + parasrt[1]);
+    npara = para.size();
+  }
+  void setnthreads(int k) override { for (Lpdf* l : kid) l->setnthreads(k); }
+  void updateom() override { for (Lpdf* l : kid) l->updateom(); redohess = true; }
+  void updatepara(const double* p, u64 n) override {
+    if (n != para.size()) throw std::range_error("wrongsized para vector");
+    for (int c = 0; c < 2; ++c) {
+      std::copy(p + parasrt[c], p + paraend[c] + 1, para.begin() + parasrt[c]);
+      kid[c]->updatepara(p + parasrt[c], paraend[c] + 1 - parasrt[c]);
+    }
+    redohess = true;
+  }
+  void updateterms(const u64* t, u64 K) override {
+    terms.assign(t, t + K * d);
+    for (Lpdf* l : kid) { l->updateterms(t, K); nterms = l->nterms; }
+    redohess = true;
+  }
+  std::vector<double> diaghess_() {
+    std::vector<double> out = kid[0]->diaghess(), h = kid[1]->diaghess();
+    for (u64 i = 0; i < out.size(); ++i) out[i] += h[i];
+    return out;
+  }
+  std::vector<double> diaghessgradhyp_() {
+    std::vector<double> out = kid[0]->diaghessgradhyp(), h = kid[1]->diaghessgradhyp();
+    for (u64 i = 0; i < out.size(); ++i) out[i] += h[i];
+    return out;
+  }
+  std::vector<double> diaghessgradpara_() {
+    std::vector<double> out(nterms * para.size(), 0.0);
+    for (int c = 0; c < 2; ++c) {
+      std::vector<double> h = kid[c]->diaghessgradpara();
+      const u64 nc = paraend[c] + 1 - parasrt[c];
+      for (u64 j = 0; j < nc; ++j) for (u64 i = 0; i < nterms; ++i) out[i + (parasrt[c] + j) * nterms] = h[i + j * nterms];
+    }
+    return out;
+  }
+  void settotdiaghess(const std::vector<double>& dh) override { totdiaghess = dh; for (Lpdf* l : kid) l->settotdiaghess(dh); }
+  void buildhess() { /* fit.cpp:252-267 */
+    if (redohess) {
+      diaghessv = diaghess_();
+      settotdiaghess(diaghessv);
+      if (domargadj) {
+        diaghessgradhypv = diaghessgradhyp_();
+        diaghessgradparav = diaghessgradpara_();
+        const u64 K = diaghessv.size(), H = diaghessgradhypv.size() / std::max<u64>(K, 1), P = para.size();
+        std::vector<double> t(K);
+        for (u64 i = 0; i < K; ++i) t[i] = std::log(diaghessv[i]);
+        val_margadj = -0.5 * obh::sum2(t.data(), K);
+        gradhyp_margadj.assign(H, 0.0);
+        for (u64 h = 0; h < H; ++h) {
+          for (u64 i = 0; i < K; ++i) t[i] = diaghessgradhypv[i + h * K] / diaghessv[i];
+          gradhyp_margadj[h] = -0.5 * obh::sum2(t.data(), K);
+        }
+        gradpara_margadj.assign(P, 0.0);
+        for (u64 h = 0; h < P; ++h) {
+          for (u64 i = 0; i < K; ++i) t[i] = diaghessgradparav[i + h * K] / diaghessv[i];
+          gradpara_margadj[h] = -0.5 * obh::sum2(t.data(), K);
+        }
+      }
+    }
+    redohess = false;
+  }
+  void update(const std::vector<double>& c) override { /* fit.cpp:323-361 */
+    coeff = c;
+    for (Lpdf* l : kid) {
+      l->compute_val = compute_val; l->compute_grad = compute_grad;
+      l->compute_gradhyp = compute_gradhyp; l->compute_gradpara = compute_gradpara;
+    }
+    for (Lpdf* l : kid) l->update(coeff);
+    if (compute_val) val = 0;
+    if (compute_grad) grad.assign(kid[0]->grad.size(), 0.0);
+    if (compute_gradhyp) gradhyp.assign(kid[0]->gradhyp.size(), 0.0);
+    if (compute_gradpara) gradpara.assign(para.size(), 0.0);
+    buildhess();
+    for (int cnt = 0; cnt < 2; ++cnt) {
+      Lpdf* l = kid[cnt];
+      if (compute_val) val += l->val;
+      if (compute_grad) for (u64 i = 0; i < grad.size(); ++i) grad[i] += l->grad[i];
+      if (compute_gradhyp) for (u64 i = 0; i < gradhyp.size(); ++i) gradhyp[i] += l->gradhyp[i];
+      if (compute_gradpara) for (u64 i = parasrt[cnt]; i <= paraend[cnt]; ++i) gradpara[i] += l->gradpara[i - parasrt[cnt]];
+    }
+    if (domargadj) { /* margadj :371-380 */
+      if (compute_val) val += val_margadj;
+      if (compute_gradhyp) for (u64 i = 0; i < gradhyp.size(); ++i) gradhyp[i] += gradhyp_margadj[i];
+      if (compute_gradpara) for (u64 i = 0; i < gradpara.size(); ++i) gradpara[i] += gradpara_margadj[i];
+    }
+  }
+  std::vector<double> hessmult(const std::vector<double>& g) override {
+    std::vector<double> out = kid[0]->hessmult(g), h = kid[1]->hessmult(g);
+    for (u64 i = 0; i < out.size(); ++i) out[i] += h[i];
+    return out;
+  }
+  std::vector<double> diaghess() override { return diaghessv; }
+  std::vector<double> diaghessgradhyp() override { return diaghessgradhypv; }
+  std::vector<double> diaghessgradpara() override { return diaghessgradparav; }
+  double paralpdf(const double* p, u64 n) const override {
+    if (n != para.size()) return -std::numeric_limits<double>::infinity();
+    double out = 0;
+    for (int c = 0; c < 2; ++c) out += kid[c]->paralpdf(p + parasrt[c], paraend[c] + 1 - parasrt[c]);
+    return out;
+  }
+  void paralpdf_grad(const double* p, u64 n, double* out) const override {
+    for (u64 i = 0; i < para.size(); ++i) out[i] = 0.0;
+    if (n != para.size()) return;
+    for (int c = 0; c < 2; ++c) kid[c]->paralpdf_grad(p + parasrt[c], paraend[c] + 1 - parasrt[c], out + parasrt[c]);
+  }
+  u64 nhyp() const override { return kid[0]->nhyp(); }
+  u64 nrow() const override { return std::max(kid[0]->nrow(), kid[1]->nrow()); }
+};
+
+struct PredGauss { /* loglik_gauss.cpp:196-227 */
+  Ctx& ctx;
+  const OuterMod* om;
+  std::vector<double> para, coeff, coeffvar;
+  std::vector<u64> terms;
+  u64 K, d;
+  int nthreads = 0;
+  std::unique_ptr<OuterBase> ob;
+  PredGauss(LoglikGauss& lk) : ctx(lk.ctx), om(lk.om), para(lk.para), coeff(lk.coeff), terms(lk.terms), K(lk.nterms), d(lk.d) {
+    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false));
+    nthreads = (int)lk.ob.nthreads;
+    if (coeff.size() != K) coeff.assign(K, 0.0);
+    if (!lk.didnotothess) {
+      coeffvar.resize(lk.totdiaghess.size());
+      for (u64 i = 0; i < coeffvar.size(); ++i) coeffvar[i] = 1 / lk.totdiaghess[i];
+    } else coeffvar.assign(coeff.size(), 0.0);
+  }
+  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false)); }
+  void mean(double* out) { ob->mm(0, terms.data(), K, coeff.data(), out); }
+  void var(double* out) {
+    ob->mm(1, terms.data(), K, coeffvar.data(), out);
+    const double c = std::exp(2 * para[0]);
+    for (u64 i = 0; i < ob->N; ++i) out[i] += c;
+  }
+};
+
+} // namespace obe

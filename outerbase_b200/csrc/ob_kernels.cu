@@ -1,0 +1,959 @@
+/*
+ * ob_kernels.cu -- hand-written sm_100a kernels of the outerbase hot path.
+ *
+ *   phi_a_kernel   Phi a  (+ fused loglik_gauss epilogues)   replaces prodmm_/domult_   src/linalg.cpp:57-131
+ *   phi_t_kernel   Phi^T r                                    replaces tprodmm_/dotmultsub_ src/linalg.cpp:286-355
+ *   (the same two kernels, fed augmented programs / gradient columns, give
+ *    prodmmge_/tprodmmge_ src/linalg.cpp:139-277,364-471 and the squared operators
+ *    of src/modandbase.cpp:784-879)
+ *   *_simple       brute-force forms in the reference's own operation order
+ *                  (fallback for programs the trie interpreter does not take, getm_ :685-715)
+ *   basis_build    cov(x,knots) . rotmat, normalise          replaces outermod::buildob + outerbase::build
+ *                                                             src/modandbase.cpp:285-327,547-626, covfuncs.cpp:113-347
+ *
+ * Layout in HBM: every N-row matrix is column-major with a leading dimension padded to
+ * a multiple of 128 rows (pad rows are zero), so a (rows x column) tile segment is one
+ * contiguous, 16-byte aligned run that a single cp.async.bulk (TMA, SASS UBLKCP) moves
+ * into shared memory.  A CTA owns row tiles of 32*R rows; the tile's used basis columns
+ * (Lcols ~ 75-100 of the M = 400-800 stored) are staged once, double buffered, and all
+ * warps of the CTA interpret their share of the terms trie on it (ob_terms.hpp).
+ */
+#include <dlfcn.h>
+
+#include "ob_device.cuh"
+
+namespace obd {
+
+using namespace obt;
+
+/* ------------------------------------------------------------------ PTX helpers */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* 1-D bulk async copy global -> shared, completion on an mbarrier (TMA engine, SASS UBLKCP) */
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+/* ------------------------------------------------------------------ kernel parameters */
+struct PhiKParams {
+  const double* const* load_src;
+  const int* col_op;
+  int ncol, nload, has_ops;
+  const uint32_t* prog;
+  const uint32_t* prog_off;
+  const uint32_t* slot_base;
+  const uint32_t* slot_real;
+  const int32_t* slot_term;
+  int nslots, nwords, prog_in_smem;
+  const double* scale;
+  int sq;
+  unsigned long long N;
+  int ntiles, nbuf;
+  unsigned off_tile, tile_doubles, off_vec, off_prog, off_part;
+  /* phi_a */
+  const double* a;
+  double* out;
+  double* w;
+  const double* y;
+  double sd;
+  double* ssq_partial;
+  int mode;
+  /* phi_t */
+  const double* win;
+  double* partial;
+};
+
+template <int R>
+__device__ __forceinline__ void load_factor(double (&f)[R], const double* bc, int lane) {
+  const double2 v0 = *reinterpret_cast<const double2*>(bc + 2 * lane);
+  f[0] = v0.x; f[1] = v0.y;
+  if constexpr (R == 4) {
+    const double2 v1 = *reinterpret_cast<const double2*>(bc + 64 + 2 * lane);
+    f[2] = v1.x; f[3] = v1.y;
+  }
+}
+template <int R>
+__device__ __forceinline__ int tile_row(int lane, int r) { return (r >> 1) * 64 + 2 * lane + (r & 1); }
+
+/* register stack of SD slots; the index is warp-uniform, the switch keeps it in registers */
+template <int R, int SD>
+__device__ __forceinline__ void stk_get(double (&dst)[R], const double (&stk)[SD][R], uint32_t e) {
+#pragma unroll
+  for (int i = 0; i < SD; ++i)
+    if (e == (uint32_t)i) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) dst[r] = stk[i][r];
+    }
+}
+template <int R, int SD>
+__device__ __forceinline__ void stk_set(double (&stk)[SD][R], uint32_t e, const double (&src)[R]) {
+#pragma unroll
+  for (int i = 0; i < SD; ++i)
+    if (e == (uint32_t)i) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) stk[i][r] = src[r];
+    }
+}
+
+/* stage one row tile: nload columns of 32*R rows each, one bulk copy per column */
+template <int R>
+__device__ __forceinline__ void issue_tile(const PhiKParams& p, double* T, uint64_t* bar, unsigned long long row0, int lane) {
+  constexpr uint32_t colbytes = 32 * R * sizeof(double);
+  fence_proxy_async();
+  if (lane == 0) mbar_expect_tx(bar, colbytes * (uint32_t)p.nload);
+  __syncwarp();
+  for (int c = lane; c < p.nload; c += 32) bulk_g2s(T + (size_t)c * (32 * R), p.load_src[c] + row0, colbytes, bar);
+}
+
+template <int R>
+__device__ __forceinline__ void transform_tile(const PhiKParams& p, double* T) {
+  constexpr int TR = 32 * R;
+  for (int idx = threadIdx.x; idx < p.ncol * TR; idx += blockDim.x) {
+    const int c = idx / TR, r = idx - c * TR;
+    const int op = p.col_op[c];
+    const double x = T[idx];
+    if ((op & 255) == COL_SQUARE) T[idx] = x * x;
+    else if ((op & 255) == COL_TWO_G_B) T[idx] = 2.0 * (x * T[(op >> 8) * TR + r]);
+  }
+}
+
+/* ------------------------------------------------------------------ Phi a
+ * One warp = one term group; lanes x R = the tile's rows.  Backward (Horner) stream. */
+template <int R, int SD>
+__global__ void __launch_bounds__(512, 1) phi_a_kernel(const PhiKParams p) {
+  constexpr int TR = 32 * R;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  double* tiles = reinterpret_cast<double*>(smem + p.off_tile);
+  double* a_sm = reinterpret_cast<double*>(smem + p.off_vec);
+  uint32_t* prog_sm = reinterpret_cast<uint32_t*>(smem + p.off_prog);
+  double* part = reinterpret_cast<double*>(smem + p.off_part);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = blockDim.x >> 5;
+
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+  for (int i = tid; i < p.nslots; i += blockDim.x) { const int t = p.slot_term[i]; a_sm[i] = t >= 0 ? p.a[t] : 0.0; }
+  if (p.prog_in_smem) for (int i = tid; i < p.nwords; i += blockDim.x) prog_sm[i] = p.prog[i];
+  __syncthreads();
+  const uint32_t* pw0 = (p.prog_in_smem ? prog_sm : p.prog) + p.prog_off[warp];
+  const int slot_hi = (int)p.slot_base[warp] + (int)p.slot_real[warp] - 1;
+
+  int tile = blockIdx.x;
+  if (warp == 0 && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
+  uint32_t phases = 0;
+  double ssq_local = 0.0;
+  for (int it = 0; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = (p.nbuf == 2) ? (it & 1) : 0;
+    const int nxt = tile + gridDim.x;
+    if (p.nbuf == 2 && warp == 0 && nxt < p.ntiles)
+      issue_tile<R>(p, tiles + (size_t)(buf ^ 1) * p.tile_doubles, &bars[buf ^ 1], (unsigned long long)nxt * TR, lane);
+    mbar_wait(&bars[buf], (phases >> buf) & 1u);
+    phases ^= (1u << buf);
+    double* T = tiles + (size_t)buf * p.tile_doubles;
+    if (p.has_ops) { transform_tile<R>(p, T); __syncthreads(); }
+
+    double cur[R], stk[SD][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) cur[r] = 0.0;
+    const uint32_t* pw = pw0;
+    int slot = slot_hi;
+    for (;;) {
+      const uint32_t w = *pw++;
+      const uint32_t op = w >> 28;
+      if (op == B_END) break;
+      const double* bc = T + (size_t)(w & 0xFFFFu) * TR;
+      if (op == B_LEAF) {
+        double f[R];
+        load_factor<R>(f, bc, lane);
+        const double av = a_sm[slot--];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] = fma(f[r], av, cur[r]);
+      } else if (op == B_CLOSE_FRESH) {
+        double f[R];
+        load_factor<R>(f, bc, lane);
+        const double av = (w & (FLAG_HAS_A << 20)) ? a_sm[slot--] : 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] = f[r] * (av + cur[r]);
+      } else if (op == B_CLOSE_LOAD) {
+        double f[R], base[R];
+        load_factor<R>(f, bc, lane);
+        const double av = (w & (FLAG_HAS_A << 20)) ? a_sm[slot--] : 0.0;
+        stk_get<R, SD>(base, stk, ((w >> 24) & 15u) - 1u);
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] = fma(f[r], av + cur[r], base[r]);
+      } else if (op == B_SAVE) {
+        stk_set<R, SD>(stk, (w >> 24) & 15u, cur);
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] = 0.0;
+      } else { /* B_ROOT */
+        const double av = a_sm[slot--];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] += av;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) part[warp * TR + tile_row<R>(lane, r)] = cur[r];
+    __syncthreads();
+    if (tid < TR) {
+      const unsigned long long row = (unsigned long long)tile * TR + tid;
+      if (row < p.N) {
+        double s = 0.0;
+        for (int g = 0; g < G; ++g) s += part[g * TR + tid];
+        double sc = p.scale[row];
+        if (p.sq) sc = sc * sc;
+        const double yv = s * sc;
+        if (p.mode == PHI_PLAIN) p.out[row] = yv;
+        else if (p.mode == PHI_UPDATE) { /* loglik_gauss::update, loglik_gauss.cpp:121-125 */
+          p.out[row] = yv;
+          const double rt = (yv - p.y[row]) / p.sd;
+          ssq_local += rt * rt;
+          p.w[row] = -1. * (rt / p.sd);
+        } else { /* loglik_gauss::hessmult, loglik_gauss.cpp:139-141 */
+          p.w[row] = (yv / p.sd) / p.sd;
+        }
+      }
+    }
+    __syncthreads();
+    if (p.nbuf == 1 && warp == 0 && nxt < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)nxt * TR, lane);
+  }
+  if (p.mode == PHI_UPDATE) { /* deterministic per-CTA sum of squared standardised residuals */
+    __syncthreads();
+    if (tid < TR) part[tid] = ssq_local;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int i = 0; i < TR; ++i) s += part[i];
+      p.ssq_partial[blockIdx.x] = s;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ Phi^T r
+ * Forward (top-down) stream; per-term row sums are reduced across the warp with an
+ * 8-term butterfly (one 64-bit exchange halves eight sums at once) and accumulated
+ * into CTA-private shared-memory slots; every slot belongs to exactly one warp. */
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+/* e[0..7]: per-lane partial sums of 8 consecutive emits.  Returns, in every lane, the
+ * full 32-lane sum of emit number ((lane>>2)&7) */
+__device__ __forceinline__ double butterfly8(double (&e)[8], int lane) {
+  double h[4], q[2];
+  const bool up16 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { /* lanes with bit4 keep emits 4..7 */
+    const double keep = up16 ? e[i + 4] : e[i];
+    const double send = up16 ? e[i] : e[i + 4];
+    h[i] = keep + shfl_xor_d(send, 16);
+  }
+  const bool up8 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double keep = up8 ? h[i + 2] : h[i];
+    const double send = up8 ? h[i] : h[i + 2];
+    q[i] = keep + shfl_xor_d(send, 8);
+  }
+  const bool up4 = lane & 4;
+  const double keep = up4 ? q[1] : q[0];
+  const double send = up4 ? q[0] : q[1];
+  double v = keep + shfl_xor_d(send, 4);
+  v += shfl_xor_d(v, 2);
+  v += shfl_xor_d(v, 1);
+  return v; /* emit index = 4*bit4 + 2*bit3 + bit2 */
+}
+
+template <int R, int SD>
+__global__ void __launch_bounds__(512, 1) phi_t_kernel(const PhiKParams p) {
+  constexpr int TR = 32 * R;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  double* tiles = reinterpret_cast<double*>(smem + p.off_tile);
+  double* acc_sm = reinterpret_cast<double*>(smem + p.off_vec);
+  uint32_t* prog_sm = reinterpret_cast<uint32_t*>(smem + p.off_prog);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+  for (int i = tid; i < p.nslots; i += blockDim.x) acc_sm[i] = 0.0;
+  if (p.prog_in_smem) for (int i = tid; i < p.nwords; i += blockDim.x) prog_sm[i] = p.prog[i];
+  __syncthreads();
+  const uint32_t* pw0 = (p.prog_in_smem ? prog_sm : p.prog) + p.prog_off[warp];
+  const int slot_lo = (int)p.slot_base[warp];
+  /* which of the 8 emits of a batch this lane owns after the butterfly, and whether it stores */
+  const int my_emit = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const bool storer = (lane & 3) == 0;
+
+  int tile = blockIdx.x;
+  if (warp == 0 && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
+  uint32_t phases = 0;
+  for (int it = 0; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = (p.nbuf == 2) ? (it & 1) : 0;
+    const int nxt = tile + gridDim.x;
+    if (p.nbuf == 2 && warp == 0 && nxt < p.ntiles)
+      issue_tile<R>(p, tiles + (size_t)(buf ^ 1) * p.tile_doubles, &bars[buf ^ 1], (unsigned long long)nxt * TR, lane);
+    /* b = basescale % a (linalg.cpp:312), zero beyond N */
+    double cur[R], stk[SD][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const unsigned long long row = (unsigned long long)tile * TR + tile_row<R>(lane, r);
+      double b = 0.0;
+      if (row < p.N) { double sc = p.scale[row]; if (p.sq) sc = sc * sc; b = sc * p.win[row]; }
+      stk[0][r] = b;
+      cur[r] = b;
+    }
+    mbar_wait(&bars[buf], (phases >> buf) & 1u);
+    phases ^= (1u << buf);
+    double* T = tiles + (size_t)buf * p.tile_doubles;
+    if (p.has_ops) { transform_tile<R>(p, T); __syncthreads(); }
+
+    const uint32_t* pw = pw0;
+    int slot = slot_lo;
+    bool done = false;
+    while (!done) {
+      double e[kEmitBatch];
+#pragma unroll
+      for (int i = 0; i < kEmitBatch; ++i) {
+        double acc = 0.0;
+        bool emitted = false;
+        while (!emitted) {
+          const uint32_t w = *pw;
+          const uint32_t op = w >> 28;
+          if (op == F_END) { done = true; break; }
+          ++pw;
+          const double* bc = T + (size_t)(w & 0xFFFFu) * TR;
+          if (op == F_LEAF) {
+            double f[R];
+            load_factor<R>(f, bc, lane);
+            acc = cur[0] * f[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc = fma(cur[r], f[r], acc);
+          } else if (op == F_DESC_CUR || op == F_DESC_STK) {
+            double f[R];
+            load_factor<R>(f, bc, lane);
+            if (op == F_DESC_STK) stk_get<R, SD>(cur, stk, ((w >> 24) & 15u) - 1u);
+#pragma unroll
+            for (int r = 0; r < R; ++r) cur[r] *= f[r];
+            if (w & (FLAG_SAVE << 20)) stk_set<R, SD>(stk, (w >> 24) & 15u, cur);
+            acc = cur[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc += cur[r];
+          } else if (op == F_ROOT) {
+            acc = stk[0][0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc += stk[0][r];
+          } else if (op == F_LOADCUR) {
+            stk_get<R, SD>(cur, stk, (w >> 24) & 15u);
+          } else { /* F_EMITZERO */
+            acc = 0.0;
+          }
+          emitted = (w & (FLAG_EMIT << 20)) != 0;
+        }
+        e[i] = acc;
+        if (done) {
+#pragma unroll
+          for (int j = i; j < kEmitBatch; ++j) e[j] = 0.0;
+          break;
+        }
+      }
+      if (done) break; /* streams are padded to whole batches, so nothing is pending here */
+      const double tot = butterfly8(e, lane);
+      if (storer) acc_sm[slot + my_emit] += tot;
+      slot += kEmitBatch;
+    }
+    __syncthreads();
+    if (p.nbuf == 1 && warp == 0 && nxt < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)nxt * TR, lane);
+  }
+  __syncthreads();
+  for (int i = tid; i < p.nslots; i += blockDim.x) p.partial[(size_t)blockIdx.x * p.nslots + i] = acc_sm[i];
+}
+
+/* out[term(slot)] = sum over CTAs, fixed order */
+__global__ void phi_t_reduce_kernel(const double* __restrict__ partial, int nblocks, int nslots,
+                                    const int32_t* __restrict__ slot_term, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  const int t = slot_term[i];
+  if (t < 0) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nslots + i];
+  out[t] = s;
+}
+
+/* ------------------------------------------------------------------ brute-force forms
+ * Operation order of the reference (linalg.cpp:70-75): temp = a_k; temp *= B columns
+ * in ascending dimension; out += temp; finally out *= basescale.  __dmul_rn/__dadd_rn
+ * keep the compiler from contracting to FMA, so phi_a_simple is BIT-EXACT against the
+ * reference's row-chunk branch. */
+__device__ __forceinline__ double col_value(const double* const* load_src, const int* col_op, uint32_t c, unsigned long long n) {
+  const double x = load_src[c][n];
+  const int op = col_op[c];
+  if ((op & 255) == COL_SQUARE) return __dmul_rn(x, x);
+  if ((op & 255) == COL_TWO_G_B) return __dmul_rn(2.0, __dmul_rn(x, load_src[op >> 8][n]));
+  return x;
+}
+
+__global__ void phi_a_simple_kernel(const double* const* load_src, const int* col_op, const uint32_t* csr_ptr,
+                                    const uint32_t* csr_col, int K, const double* a, const double* scale, int sq,
+                                    unsigned long long N, double* out) {
+  const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) {
+    double t = a[k];
+    for (uint32_t j = csr_ptr[k]; j < csr_ptr[k + 1]; ++j) t = __dmul_rn(t, col_value(load_src, col_op, csr_col[j], n));
+    acc = __dadd_rn(acc, t);
+  }
+  double sc = scale[n];
+  if (sq) sc = __dmul_rn(sc, sc);
+  out[n] = __dmul_rn(acc, sc);
+}
+
+__global__ void phi_t_simple_kernel(const double* const* load_src, const int* col_op, const uint32_t* csr_ptr,
+                                    const uint32_t* csr_col, int K, const double* w, const double* scale, int sq,
+                                    unsigned long long N, double* out /* K, pre-zeroed */) {
+  const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double b = 0.0;
+  if (n < N) { double sc = scale[n]; if (sq) sc = __dmul_rn(sc, sc); b = __dmul_rn(sc, w[n]); }
+  for (int k = 0; k < K; ++k) {
+    double t = b;
+    if (n < N)
+      for (uint32_t j = csr_ptr[k]; j < csr_ptr[k + 1]; ++j) t = __dmul_rn(t, col_value(load_src, col_op, csr_col[j], n));
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) t += shfl_xor_d(t, m);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&out[k], t);
+  }
+}
+
+__global__ void getmat_kernel(const double* const* load_src, const int* col_op, const uint32_t* csr_ptr,
+                              const uint32_t* csr_col, int K, const double* scale, int sq, unsigned long long N,
+                              double* out, unsigned long long ldo) {
+  const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double sc = scale[n];
+  if (sq) sc = __dmul_rn(sc, sc);
+  for (int k = blockIdx.y; k < K; k += gridDim.y) {
+    double t = 1.0;
+    for (uint32_t j = csr_ptr[k]; j < csr_ptr[k + 1]; ++j) t = __dmul_rn(t, col_value(load_src, col_op, csr_col[j], n));
+    out[n + (unsigned long long)k * ldo] = __dmul_rn(t, sc);
+  }
+}
+
+__global__ void sum_partials_kernel(const double* partial, int n, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    out[0] = s;
+  }
+}
+
+__global__ void fill_kernel(double* p, unsigned long long n, double v) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+/* per-block partial dot products, fixed tree */
+__global__ void dot_partials_kernel(const double* a, const double* b, unsigned long long n, double* partial) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    s = fma(a[i], b[i], s);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) { if ((int)threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st]; __syncthreads(); }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+/* ------------------------------------------------------------------ covariance + basis build */
+struct CovPt { double t, s; }; /* mat25/pow: t = transformed x, s = log(x)*t ; ang: t = sin/rho_s, s = cos/rho_c */
+
+__device__ __forceinline__ CovPt cov_transform_dev(int kind, double h0, double h1, double x) {
+  CovPt p;
+  if (kind == obh::COV_MAT25) { p.t = x / exp(2. * h0); p.s = 0.0; }
+  else if (kind == obh::COV_MAT25POW) {
+    const double powv = exp(0.25 * h1);
+    p.t = pow(x, powv) / exp(2. * h0 + 0.25 * h1);
+    p.s = log(x) * p.t;
+  } else { p.t = sin(x) / exp(2. * h0); p.s = cos(x) / exp(2. * h1); }
+  return p;
+}
+/* covf_*::cov and cov_gradhyp for one pair, covfuncs.cpp:113-150,197-243,285-347 */
+template <bool GRAD>
+__device__ __forceinline__ void cov_pair_dev(int kind, double h1, const CovPt& a, const CovPt& b, double& v, double& g0, double& g1) {
+  if (kind == obh::COV_MAT25ANG) {
+    const double hs = a.t - b.t, hc = a.s - b.s;
+    const double t = sqrt(hs * hs + hc * hc);
+    const double e = exp(-t);
+    v = (1 + t + (t * t) / 3) * e;
+    if (GRAD) { const double wv = e * (t + 1); g0 = ((2. / 3) * (hs * hs)) * wv; g1 = ((2. / 3) * (hc * hc)) * wv; }
+    return;
+  }
+  double h = a.t - b.t;
+  const double ah = fabs(h), e = exp(-ah);
+  v = (1 + ah + (ah * ah) / 3) * e;
+  if (!GRAD) return;
+  const double h2 = (h * (1 + ah)) * e;
+  if (kind == obh::COV_MAT25) { g0 = (2. / 3) * (h * h2); g1 = 0.0; return; }
+  const double powv = exp(0.25 * h1);
+  double s1 = a.s - b.s;
+  s1 *= (-(0.25 * powv / 3)) * h2;
+  h *= h2;
+  g1 = s1 + (0.25 / 3) * h;
+  g0 = (2. / 3) * h;
+}
+
+__global__ void cov_kernel(int kind, double h0, double h1, const double* x1, unsigned long long n1, const double* x2,
+                           unsigned long long n2, double* out, double* outg) {
+  const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n1 * n2) return;
+  const unsigned long long i = idx % n1, j = idx / n1;
+  const CovPt a = cov_transform_dev(kind, h0, h1, x1[i]), b = cov_transform_dev(kind, h0, h1, x2[j]);
+  double v, g0 = 0, g1 = 0;
+  if (outg) cov_pair_dev<true>(kind, h1, a, b, v, g0, g1);
+  else cov_pair_dev<false>(kind, h1, a, b, v, g0, g1);
+  out[idx] = v;
+  if (outg) {
+    outg[idx] = g0;
+    if (kind != obh::COV_MAT25) outg[idx + n1 * n2] = g1;
+  }
+}
+
+struct BuildKParams {
+  int kind, m, nh, mp; /* mp: padded row length of the transposed rotation blocks in smem */
+  double h0, h1;
+  const double* knots;  /* this dim's m knots */
+  const double* x;      /* this dim's column of x */
+  const double* rot;    /* m x m block, column-major, ld rot_ld */
+  const double* rotg0;
+  const double* rotg1;
+  unsigned long long rot_ld;
+  double* bm;           /* basemat + col_off*ld */
+  double* bg0;
+  double* bg1;
+  double* scalecol;     /* basescalemat column */
+  unsigned long long N, ld;
+  int dograd;
+};
+
+/* ROWS rows per CTA, 256 threads = ROWS x (256/ROWS) column groups, 4 columns per group step.
+ * smem: rotT[(1+nh)][m][mp] (row p, column j contiguous), C[(1+nh)][m][ROWS], knot/row transforms. */
+template <int ROWS>
+__global__ void __launch_bounds__(256) basis_build_kernel(const BuildKParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const int m = p.m, mp = p.mp, nh = p.dograd ? p.nh : 0;
+  double* rotT = sm;                                   /* (1+nh) * m * mp */
+  double* Cs = rotT + (size_t)(1 + nh) * m * mp;       /* (1+nh) * m * ROWS */
+  double* kt = Cs + (size_t)(1 + nh) * m * ROWS;       /* 2*m knot transforms */
+  double* xt = kt + 2 * m;                             /* 2*ROWS row transforms */
+  const int tid = threadIdx.x;
+  const unsigned long long row0 = (unsigned long long)blockIdx.x * ROWS;
+
+  for (int idx = tid; idx < m * m; idx += 256) {
+    const int pp = idx % m, j = idx / m; /* column-major source: element (pp, j) */
+    rotT[(size_t)pp * mp + j] = p.rot[pp + (unsigned long long)j * p.rot_ld];
+    if (nh > 0) rotT[(size_t)(m + pp) * mp + j] = p.rotg0[pp + (unsigned long long)j * p.rot_ld];
+    if (nh > 1) rotT[(size_t)(2 * m + pp) * mp + j] = p.rotg1[pp + (unsigned long long)j * p.rot_ld];
+  }
+  for (int idx = tid; idx < m; idx += 256) {
+    const CovPt c = cov_transform_dev(p.kind, p.h0, p.h1, p.knots[idx]);
+    kt[idx] = c.t; kt[m + idx] = c.s;
+  }
+  for (int idx = tid; idx < ROWS; idx += 256) {
+    const unsigned long long row = row0 + idx;
+    CovPt c{0.0, 0.0};
+    if (row < p.N) c = cov_transform_dev(p.kind, p.h0, p.h1, p.x[row]);
+    xt[idx] = c.t; xt[ROWS + idx] = c.s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * ROWS; idx += 256) {
+    const int r = idx % ROWS, pp = idx / ROWS;
+    const CovPt a{xt[r], xt[ROWS + r]}, b{kt[pp], kt[m + pp]};
+    double v, g0 = 0, g1 = 0;
+    if (nh > 0) cov_pair_dev<true>(p.kind, p.h1, a, b, v, g0, g1);
+    else cov_pair_dev<false>(p.kind, p.h1, a, b, v, g0, g1);
+    Cs[(size_t)pp * ROWS + r] = v;
+    if (nh > 0) Cs[(size_t)(m + pp) * ROWS + r] = g0;
+    if (nh > 1) Cs[(size_t)(2 * m + pp) * ROWS + r] = g1;
+  }
+  __syncthreads();
+
+  constexpr int NCG = 256 / ROWS;
+  const int r = tid % ROWS, cg = tid / ROWS;
+  const unsigned long long row = row0 + r;
+  const bool live = row < p.N;
+  /* column 0 of the projected basis: the per-row scale P_l[:,0] (modandbase.cpp:297,572) */
+  double p0 = 0.0;
+  for (int pp = 0; pp < m; ++pp) p0 = fma(Cs[(size_t)pp * ROWS + r], rotT[(size_t)pp * mp], p0);
+  if (cg == 0 && row < p.ld) p.scalecol[row] = live ? p0 : 0.0;
+  for (int j0 = cg * 4; j0 < m; j0 += NCG * 4) {
+    double acc[4] = {0, 0, 0, 0}, s1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, s2[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int pp = 0; pp < m; ++pp) {
+      const double c = Cs[(size_t)pp * ROWS + r];
+      const double* rr = rotT + (size_t)pp * mp + j0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(c, rr[q], acc[q]);
+      if (nh > 0) {
+        const double cg0 = Cs[(size_t)(m + pp) * ROWS + r];
+        const double* rg = rotT + (size_t)(m + pp) * mp + j0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s1[0][q] = fma(cg0, rr[q], s1[0][q]); s2[0][q] = fma(c, rg[q], s2[0][q]); }
+      }
+      if (nh > 1) {
+        const double cg1 = Cs[(size_t)(2 * m + pp) * ROWS + r];
+        const double* rg = rotT + (size_t)(2 * m + pp) * mp + j0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s1[1][q] = fma(cg1, rr[q], s1[1][q]); s2[1][q] = fma(c, rg[q], s2[1][q]); }
+      }
+    }
+    if (row < p.ld) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        if (j >= m) break;
+        double v = 0.0;
+        if (live) v = (j == 0) ? 1.0 : acc[q] / p0;
+        p.bm[row + (unsigned long long)j * p.ld] = v;
+        if (nh > 0) p.bg0[row + (unsigned long long)j * p.ld] = live ? (s1[0][q] + s2[0][q]) / p0 : 0.0;
+        if (nh > 1) p.bg1[row + (unsigned long long)j * p.ld] = live ? (s1[1][q] + s2[1][q]) / p0 : 0.0;
+      }
+    }
+  }
+}
+
+/* basescale = prod_l P_l[:,0], multiplied in dimension order (modandbase.cpp:573) */
+__global__ void basescale_kernel(const double* scalemat, unsigned long long ld, int d, unsigned long long N, double* scale) {
+  const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= ld) return;
+  double s = 1.0;
+  for (int l = 0; l < d; ++l) s = __dmul_rn(s, scalemat[n + (unsigned long long)l * ld]);
+  scale[n] = n < N ? s : 0.0;
+}
+
+__global__ void getbase_kernel(const double* basemat, const double* scalecol, unsigned long long N, unsigned long long ld,
+                               unsigned long long col0, unsigned long long m, double* out) {
+  const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * m) return;
+  const unsigned long long n = idx % N, j = idx / N;
+  out[idx] = basemat[n + (col0 + j) * ld] * scalecol[n];
+}
+
+/* FP64 FMA micro-benchmark: the roofline denominator for the Phi kernels, measured on the
+ * box the bench runs on (MEASURED_PEAKS.json has no FP64 entry).  16 independent DFMA chains
+ * per thread, 8 warps x 4 CTAs per SM. */
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + i + threadIdx.x * 1e-3;
+  const double m = 1.0 - 1e-9, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456) out[blockIdx.x] = s; /* never true: keeps the chains alive */
+}
+
+double measure_fp64_peak(Ctx& c) {
+  DevBuf<double> sink;
+  sink.ensure(4096);
+  const int grid = c.sms * 8, iters = 20000;
+  cudaEvent_t e0, e1;
+  OB_CUDA(cudaEventCreate(&e0)); OB_CUDA(cudaEventCreate(&e1));
+  fp64_peak_kernel<<<grid, 256, 0, c.stream>>>(sink.p, 2000, 1.0); /* warm-up */
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    OB_CUDA(cudaEventRecord(e0, c.stream));
+    fp64_peak_kernel<<<grid, 256, 0, c.stream>>>(sink.p, iters, 1.0 + rep);
+    OB_CUDA(cudaEventRecord(e1, c.stream));
+    OB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    OB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 16.0 * iters * 256.0 * grid;
+    best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  c.launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return best;
+}
+
+/* ------------------------------------------------------------------ context */
+NcclApi& NcclApi::get() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+    if (api.handle) {
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+    }
+  }
+  return api;
+}
+
+Ctx::Ctx(int dev) : device(dev) {
+  int count = 0;
+  const cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw NoGpuError("no CUDA device visible: outerbase_b200 has no CPU fallback");
+  if (dev < 0 || dev >= count) throw NoGpuError("CUDA device index out of range");
+  OB_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  OB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) throw NoGpuError(std::string("outerbase_b200 kernels are built for sm_100a only, found ") + prop.name);
+  sms = prop.multiProcessorCount;
+  smem_optin = prop.sharedMemPerBlockOptin;
+  OB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  OB_CUDA(cudaMallocHost(&pinned, 4096 * sizeof(double)));
+}
+
+Ctx::~Ctx() {
+  if (comm && NcclApi::get().CommDestroy) NcclApi::get().CommDestroy(comm);
+  if (pinned) cudaFreeHost(pinned);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void Ctx::allreduce_sum(double* buf, size_t n) {
+  if (nranks <= 1 || !comm) return;
+  NcclApi& api = NcclApi::get();
+  const int rc = api.AllReduce(buf, buf, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
+  if (rc != 0) throw NcclError(std::string("ncclAllReduce: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+}
+
+void DevProgram::upload(cudaStream_t s) {
+  fwd.upload(host.fwd, s); bwd.upload(host.bwd, s);
+  fwd_off.upload(host.fwd_off, s); bwd_off.upload(host.bwd_off, s);
+  slot_base.upload(host.slot_base, s); slot_real.upload(host.slot_real, s);
+  slot_term.upload(host.slot_term, s);
+  csr_ptr.upload(host.csr_ptr, s); csr_col.upload(host.csr_col, s);
+}
+
+/* ------------------------------------------------------------------ launchers */
+static void check_launch(Ctx& c, const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
+  c.launches++;
+}
+
+int phi_grid(const Ctx& c, u64 N, int tile_rows) {
+  const u64 ntiles = (N + tile_rows - 1) / tile_rows;
+  return (int)std::max<u64>(1, std::min<u64>(ntiles, (u64)c.sms));
+}
+
+struct PhiGeom {
+  int R = 0, nbuf = 0, G = 16;
+  size_t smem = 0;
+  unsigned off_tile, tile_doubles, off_vec, off_prog, off_part;
+  int prog_in_smem = 0;
+};
+
+/* choose rows per lane / buffering so that the staged tile fits the 227 KB of the SM */
+static PhiGeom phi_geometry(const Ctx& c, const DevProgram& pr, const ColTable& ct, bool is_a, u64 N) {
+  const size_t nwords = is_a ? pr.host.bwd.size() : pr.host.fwd.size();
+  const size_t vec_bytes = ((pr.host.nslots() * sizeof(double) + 127) / 128) * 128;
+  const int Rs[2] = {4, 2};
+  for (int pass = 0; pass < 2; ++pass)      /* pass 0: program copied to smem too */
+    for (int nbuf = 2; nbuf >= 1; --nbuf)
+      for (int ri = 0; ri < 2; ++ri) {
+        const int R = Rs[ri], TR = 32 * R;
+        if (R == 4 && N <= (u64)c.sms * 64) continue; /* small inputs: finer tiles fill more SMs */
+        PhiGeom g;
+        g.R = R; g.nbuf = nbuf; g.G = pr.host.G;
+        g.off_tile = 128;
+        g.tile_doubles = (unsigned)(ct.nload * TR);
+        size_t off = g.off_tile + (size_t)nbuf * g.tile_doubles * sizeof(double);
+        g.off_vec = (unsigned)off; off += vec_bytes;
+        g.off_prog = (unsigned)off;
+        g.prog_in_smem = (pass == 0);
+        if (g.prog_in_smem) off += ((nwords * 4 + 127) / 128) * 128;
+        g.off_part = (unsigned)off;
+        if (is_a) off += (size_t)g.G * TR * sizeof(double);
+        g.smem = off;
+        if (g.smem <= c.smem_optin) return g;
+      }
+  PhiGeom none;
+  return none;
+}
+
+static void fill_params(PhiKParams& p, const PhiPlan& pl, const PhiGeom& g, bool is_a) {
+  const DevProgram& pr = *pl.prog;
+  p.load_src = pl.cols->load_src.p; p.col_op = pl.cols->col_op.p;
+  p.ncol = pl.cols->ncol; p.nload = pl.cols->nload; p.has_ops = pl.cols->has_ops ? 1 : 0;
+  p.prog = is_a ? pr.bwd.p : pr.fwd.p;
+  p.prog_off = is_a ? pr.bwd_off.p : pr.fwd_off.p;
+  p.slot_base = pr.slot_base.p; p.slot_real = pr.slot_real.p; p.slot_term = pr.slot_term.p;
+  p.nslots = (int)pr.host.nslots();
+  p.nwords = (int)(is_a ? pr.host.bwd.size() : pr.host.fwd.size());
+  p.prog_in_smem = g.prog_in_smem;
+  p.scale = pl.scale; p.sq = pl.sq; p.N = pl.N;
+  p.ntiles = (int)((pl.N + 32 * g.R - 1) / (32 * g.R));
+  p.nbuf = g.nbuf;
+  p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles; p.off_vec = g.off_vec; p.off_prog = g.off_prog; p.off_part = g.off_part;
+}
+
+template <class Kern>
+static void set_smem(Kern k, size_t bytes) {
+  OB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void launch_phi_a(Ctx& c, const PhiPlan& pl, const PhiAArgs& a, Workspace& ws, int* grid_out) {
+  const DevProgram& pr = *pl.prog;
+  if (pl.N == 0) { if (grid_out) *grid_out = 0; return; }
+  PhiGeom g;
+  if (pr.host.fast_ok) g = phi_geometry(c, pr, *pl.cols, true, pl.N);
+  if (g.R == 0) { /* brute-force form */
+    if (a.mode != PHI_PLAIN) throw std::logic_error("fused epilogues need the trie kernel");
+    const int bs = 128;
+    phi_a_simple_kernel<<<(unsigned)((pl.N + bs - 1) / bs), bs, 0, c.stream>>>(
+        pl.cols->load_src.p, pl.cols->col_op.p, pr.csr_ptr.p, pr.csr_col.p, (int)pr.host.K, a.a, pl.scale, pl.sq, pl.N, a.out);
+    check_launch(c, "phi_a_simple_kernel");
+    if (grid_out) *grid_out = 0;
+    return;
+  }
+  PhiKParams p{};
+  fill_params(p, pl, g, true);
+  p.a = a.a; p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
+  const int grid = phi_grid(c, pl.N, 32 * g.R);
+  if (a.mode == PHI_UPDATE) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
+#define OB_LAUNCH_A(RR, SS) { set_smem(phi_a_kernel<RR, SS>, g.smem); phi_a_kernel<RR, SS><<<grid, 32 * g.G, g.smem, c.stream>>>(p); }
+  const int sd = pr.host.bwd_stack;
+  if (g.R == 4) { if (sd <= 4) OB_LAUNCH_A(4, 4) else OB_LAUNCH_A(4, 8) }
+  else { if (sd <= 4) OB_LAUNCH_A(2, 4) else OB_LAUNCH_A(2, 8) }
+#undef OB_LAUNCH_A
+  check_launch(c, "phi_a_kernel");
+  if (grid_out) *grid_out = grid;
+}
+
+void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Workspace& ws) {
+  const DevProgram& pr = *pl.prog;
+  const int K = (int)pr.host.K;
+  if (K == 0) return;
+  if (pl.N == 0) { launch_fill(c, out, K, 0.0); return; }
+  PhiGeom g;
+  if (pr.host.fast_ok) g = phi_geometry(c, pr, *pl.cols, false, pl.N);
+  if (g.R == 0) {
+    launch_fill(c, out, K, 0.0);
+    const int bs = 128;
+    phi_t_simple_kernel<<<(unsigned)((pl.N + bs - 1) / bs), bs, 0, c.stream>>>(
+        pl.cols->load_src.p, pl.cols->col_op.p, pr.csr_ptr.p, pr.csr_col.p, K, w, pl.scale, pl.sq, pl.N, out);
+    check_launch(c, "phi_t_simple_kernel");
+    return;
+  }
+  PhiKParams p{};
+  fill_params(p, pl, g, false);
+  const int grid = phi_grid(c, pl.N, 32 * g.R);
+  p.win = w;
+  p.partial = ws.partial.ensure((size_t)grid * p.nslots);
+#define OB_LAUNCH_T(RR, SS) { set_smem(phi_t_kernel<RR, SS>, g.smem); phi_t_kernel<RR, SS><<<grid, 32 * g.G, g.smem, c.stream>>>(p); }
+  const int sd = pr.host.fwd_stack;
+  if (g.R == 4) { if (sd <= 4) OB_LAUNCH_T(4, 4) else OB_LAUNCH_T(4, 8) }
+  else { if (sd <= 4) OB_LAUNCH_T(2, 4) else OB_LAUNCH_T(2, 8) }
+#undef OB_LAUNCH_T
+  check_launch(c, "phi_t_kernel");
+  phi_t_reduce_kernel<<<(p.nslots + 127) / 128, 128, 0, c.stream>>>(p.partial, grid, p.nslots, pr.slot_term.p, out);
+  check_launch(c, "phi_t_reduce_kernel");
+}
+
+void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo) {
+  const DevProgram& pr = *pl.prog;
+  if (pl.N == 0 || pr.host.K == 0) return;
+  const int bs = 128;
+  dim3 grid((unsigned)((pl.N + bs - 1) / bs), (unsigned)std::min<u64>(pr.host.K, 32768));
+  getmat_kernel<<<grid, bs, 0, c.stream>>>(pl.cols->load_src.p, pl.cols->col_op.p, pr.csr_ptr.p, pr.csr_col.p, (int)pr.host.K,
+                                          pl.scale, pl.sq, pl.N, out, ldo);
+  check_launch(c, "getmat_kernel");
+}
+
+void launch_sum_partials(Ctx& c, const double* partial, int n, double* out) {
+  sum_partials_kernel<<<1, 32, 0, c.stream>>>(partial, n, out);
+  check_launch(c, "sum_partials_kernel");
+}
+
+void launch_fill(Ctx& c, double* p, u64 n, double v) {
+  if (n == 0) return;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(p, n, v);
+  check_launch(c, "fill_kernel");
+}
+
+void launch_dot_partials(Ctx& c, const double* a, const double* b, u64 n, double* partial, int* nblocks) {
+  const int nb = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)c.sms * 4));
+  dot_partials_kernel<<<nb, 256, 0, c.stream>>>(a, b, n, partial);
+  check_launch(c, "dot_partials_kernel");
+  *nblocks = nb;
+}
+
+void launch_cov(Ctx& c, int kind, const double* hyp, const double* x1, u64 n1, const double* x2, u64 n2, double* out, double* outg) {
+  if (n1 * n2 == 0) return;
+  const double h1 = (kind == obh::COV_MAT25) ? 0.0 : hyp[1];
+  cov_kernel<<<(unsigned)((n1 * n2 + 255) / 256), 256, 0, c.stream>>>(kind, hyp[0], h1, x1, n1, x2, n2, out, outg);
+  check_launch(c, "cov_kernel");
+}
+
+void launch_basis_build(Ctx& c, const std::vector<BuildDims>& dims, const double* x_dev, u64 N, u64 ld, const double* knots_dev,
+                        const double* rot_dev, u64 rot_ld, const double* rotg_dev, double* basemat, double* basematge,
+                        double* scalemat, double* scale, bool dograd) {
+  if (ld == 0) return;
+  for (size_t l = 0; l < dims.size(); ++l) {
+    const BuildDims& D = dims[l];
+    BuildKParams p{};
+    p.kind = D.kind; p.m = D.m; p.nh = D.nh; p.mp = ((D.m + 3) / 4) * 4 + 4;
+    p.h0 = D.hyp[0]; p.h1 = D.hyp[1];
+    p.knots = knots_dev + D.knot_off;
+    p.x = x_dev + l * ld;
+    p.rot = rot_dev + D.rot_off * rot_ld;
+    p.rot_ld = rot_ld;
+    p.rotg0 = dograd && D.nh > 0 ? rotg_dev + D.rotg_off[0] * rot_ld : nullptr;
+    p.rotg1 = dograd && D.nh > 1 ? rotg_dev + D.rotg_off[1] * rot_ld : nullptr;
+    p.bm = basemat + D.col_off * ld;
+    p.bg0 = dograd && D.nh > 0 ? basematge + D.ge_off[0] * ld : nullptr;
+    p.bg1 = dograd && D.nh > 1 ? basematge + D.ge_off[1] * ld : nullptr;
+    p.scalecol = scalemat + l * ld;
+    p.N = N; p.ld = ld; p.dograd = dograd ? 1 : 0;
+    const int nh = dograd ? D.nh : 0;
+    auto need = [&](int rows) {
+      return ((size_t)(1 + nh) * D.m * p.mp + (size_t)(1 + nh) * D.m * rows + 2 * D.m + 2 * rows) * sizeof(double);
+    };
+    if (need(64) <= c.smem_optin) {
+      set_smem(basis_build_kernel<64>, need(64));
+      basis_build_kernel<64><<<(unsigned)((ld + 63) / 64), 256, need(64), c.stream>>>(p);
+    } else if (need(32) <= c.smem_optin) {
+      set_smem(basis_build_kernel<32>, need(32));
+      basis_build_kernel<32><<<(unsigned)((ld + 31) / 32), 256, need(32), c.stream>>>(p);
+    } else throw std::range_error("too many knots in one dimension for the basis-build kernel");
+    check_launch(c, "basis_build_kernel");
+  }
+  basescale_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, c.stream>>>(scalemat, ld, (int)dims.size(), N, scale);
+  check_launch(c, "basescale_kernel");
+}
+
+void launch_getbase(Ctx& c, const double* basemat, const double* scalecol, u64 N, u64 ld, u64 col0, u64 m, double* out) {
+  if (N * m == 0) return;
+  getbase_kernel<<<(unsigned)((N * m + 255) / 256), 256, 0, c.stream>>>(basemat, scalecol, N, ld, col0, m, out);
+  check_launch(c, "getbase_kernel");
+}
+
+} // namespace obd

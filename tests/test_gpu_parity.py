@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle.
+
+Stage-wise with shared inputs (SURVEY 7 "hard parts"): (i) the host eigenbasis and the
+`terms` table are bit-identical in both paths (tests/test_host_model.py); (ii) the matvec
+kernels are checked on bit-identical `basemat` uploaded from the oracle through the
+stateless linalg.h seam -- tolerance 1e-12 relative (north_star); (iii) the basis-build
+kernel is checked per element against the forward-error bound of its own contraction.
+Shapes are the reference's (tests/testthat/test-obombasic.R, test-obomgrad.R, test-lpdf.R):
+(N,K) in {15x20, 200x100, 10000x100, 200x1000, 10000x2000}, d = 8.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+MATVEC_TOL = 1e-12  # north_star: matvecs within 1e-12 relative in fp64
+SHAPES = [(15, 20), (200, 100), (10000, 100), (200, 1000), (10000, 2000)]
+
+
+def oracle_basis(oracle, N, K, **kw):
+    om, x, y, terms, rng = make_problem(oracle, N, K, **kw)
+    ob = oracle.outerbase(om, x)
+    return dict(om=om, x=x, y=y, terms=terms, rng=rng, ob=ob, bm=ob.real("basemat"), bs=ob.real("basescale"),
+                bg=ob.real("basemat_gradhyp"), kp=om.index("knotptst"), gest=om.index("gest"), hm=om.index("hypmatch"))
+
+
+@pytest.mark.parametrize("name,hyp", [("mat25", [0.3]), ("mat25pow", [-0.4, 0.6]), ("mat25ang", [0.2, -0.5])])
+def test_cov_and_gradhyp(gpu, oracle, name, hyp):
+    rng = np.random.default_rng(7)
+    hi = 6.28 if name == "mat25ang" else 1.0
+    x1, x2 = rng.uniform(0.001, hi, 257), rng.uniform(0.001, hi, 40)
+    assert relerr(gpu.covf_cov(name, hyp, x1, x2), oracle.covf_cov(name, hyp, x1, x2)) < 1e-13
+    assert relerr(gpu.covf_cov_gradhyp(name, hyp, x1, x2), oracle.covf_cov_gradhyp(name, hyp, x1, x2)) < 1e-12
+
+
+@pytest.mark.parametrize("N,K", SHAPES)
+def test_seam_matvecs_on_oracle_basis(gpu, oracle, N, K):
+    """prodmm_/tprodmm_ (linalg.cpp:102-131,303-355) on bit-identical inputs."""
+    o = oracle_basis(oracle, N, K)
+    terms, rng = o["terms"], o["rng"]
+    a = np.sqrt(o["om"].getvar(terms) / 20) * rng.normal(size=K)
+    r = rng.normal(size=N)
+    assert relerr(gpu.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
+    assert relerr(gpu.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+
+
+@pytest.mark.parametrize("N,K", [(200, 100), (10000, 100), (200, 1000)])
+def test_seam_gradhyp_on_oracle_basis(gpu, oracle, N, K):
+    """prodmmge_/tprodmmge_ (linalg.cpp:225-277,394-471) via augmented programs."""
+    o = oracle_basis(oracle, N, K)
+    terms, rng = o["terms"], o["rng"]
+    a = rng.normal(size=K) / 100
+    r = rng.normal(size=N)
+    out, outge = gpu.prodmmge(terms, a, o["bm"], o["bs"], o["kp"], o["bg"], o["gest"], o["hm"])
+    ro, rge = o["ob"]._mmge(0, terms, a)
+    assert relerr(out, ro) < MATVEC_TOL
+    assert relerr(outge, rge) < 1e-11
+    out, outge = gpu.tprodmmge(terms, r, o["bm"], o["bs"], o["kp"], o["bg"], o["gest"], o["hm"])
+    ro, rge = o["ob"]._tmmge(0, terms, r)
+    assert relerr(out, ro) < MATVEC_TOL
+    assert relerr(outge, rge) < 1e-11
+
+
+def test_seam_multi_rhs_and_getm(gpu, oracle):
+    """prodmm_(mat)/tprodmm_(mat)/getm_ (linalg.cpp:527-557,583-637,685-715)."""
+    o = oracle_basis(oracle, 300, 60)
+    terms, rng = o["terms"], o["rng"]
+    A = np.asfortranarray(rng.normal(size=(60, 5)))
+    R = np.asfortranarray(rng.normal(size=(300, 3)))
+    assert relerr(gpu.prodmm(terms, A, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, A)) < MATVEC_TOL
+    assert relerr(gpu.tprodmm(terms, R, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, R)) < MATVEC_TOL
+    G = gpu.getm(terms, o["bm"], o["bs"], o["kp"])
+    np.testing.assert_array_equal(G, o["ob"].getmat(terms))  # same operation order: bit-exact
+
+
+def test_bruteforce_path_is_bit_exact(gpu, oracle):
+    """A terms table with a duplicated row is refused by the trie compiler and runs on the
+    brute-force kernel, which follows linalg.cpp:70-75 operation by operation."""
+    o = oracle_basis(oracle, 10000, 100)
+    terms = np.asfortranarray(np.vstack([o["terms"], o["terms"][5:6]]))
+    a = o["rng"].normal(size=101)
+    got = gpu.prodmm(terms, a, o["bm"], o["bs"], o["kp"])
+    np.testing.assert_array_equal(got, o["ob"].matmul(terms, a))
+    r = o["rng"].normal(size=10000)
+    assert relerr(gpu.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+
+
+@pytest.mark.parametrize("covs", [None, ["mat25pow"] * 8, ["mat25ang", "mat25", "mat25pow", "mat25", "mat25", "mat25", "mat25", "mat25pow"]])
+def test_basis_build(gpu, oracle, covs):
+    """outerbase::build + outermod::buildob (modandbase.cpp:285-327,547-626).  Column j of
+    B_l is a length-m contraction divided by column 0; both sides are judged against the
+    contraction's own forward-error bound  gamma * sum_p |cov_p * rot_pj| / |P0|."""
+    N, K = 700, 50
+    omo, x, y, terms, rng = make_problem(oracle, N, K, covs=covs)
+    omg, *_ = make_problem(gpu, N, K, covs=covs)
+    hyp = omo.gethyp() + 0.05 * np.cos(np.arange(omo.gethyp().size))
+    omo.updatehyp(hyp); omg.updatehyp(hyp)
+    if covs and covs[0] == "mat25ang":
+        x = np.asfortranarray(x); x[:, 0] *= 6.0
+        kn = [np.arange(0.001, 0.999, 0.025)] * 8
+        kn[0] = np.linspace(0.05, 6.2, 40)
+        omo.setknot(kn); omg.setknot(kn)
+    obo, obg = oracle.outerbase(omo, x), gpu.outerbase(omg, x)
+    kp = omo.index("knotptst")
+    rot = omo.real("rotmat")
+    np.testing.assert_array_equal(rot, omg.real("rotmat"))
+    bo, bg = obo.real("basemat"), obg.real("basemat")
+    so, sg = obo.real("basescalemat"), obg.real("basescalemat")
+    assert relerr(sg, so) < 1e-10
+    assert relerr(obg.real("basescale"), obo.real("basescale")) < 1e-9
+    names = covs or (["mat25pow"] + ["mat25"] * 7)
+    eps = np.finfo(float).eps
+    for l in range(8):
+        m = int(kp[l + 1] - kp[l])
+        C = np.abs(oracle.covf_cov(names[l], hyp[omo.index("hypst")[l]:omo.index("hypst")[l + 1]], x[:, l], omo.real("knotpt")[kp[l]:kp[l + 1]]))
+        bound = (C @ np.abs(rot[:m, kp[l]:kp[l + 1]])) / np.abs(so[:, [l]])  # N x m
+        err = np.abs(bg[:, kp[l]:kp[l + 1]] - bo[:, kp[l]:kp[l + 1]])
+        # a few units of m*eps times the magnitude of the summed terms (+ the same for the divisor)
+        assert np.all(err <= 8 * m * eps * (bound + np.abs(bo[:, kp[l]:kp[l + 1]]) * bound[:, [0]])), f"dim {l}"
+    # gradient blocks: same criterion, looser constant; checked through their effect below
+    go, gg = obo.real("basemat_gradhyp"), obg.real("basemat_gradhyp")
+    used = np.abs(go) > 0
+    assert np.median(np.abs(gg - go)[used] / np.abs(go)[used]) < 1e-9
+    # getbase = un-normalised P_l (modandbase.cpp:634-639)
+    assert relerr(obg.getbase(3)[:, :6], obo.getbase(3)[:, :6]) < 1e-9
+
+
+@pytest.mark.parametrize("N,K", [(15, 20), (200, 100), (10000, 2000)])
+def test_outerbase_end_to_end(gpu, oracle, N, K):
+    """new(outerbase, om, x); matmul/tmatmul/getmat as test-obombasic.R:46-60 -- own basis on both sides."""
+    omo, x, y, terms, rng = make_problem(oracle, N, K)
+    omg, *_ = make_problem(gpu, N, K)
+    np.testing.assert_array_equal(terms, omg.selectterms(K))  # terms bit-exact
+    obo, obg = oracle.outerbase(omo, x), gpu.outerbase(omg, x)
+    theta = np.sqrt(omo.getvar(terms) / 20) * rng.normal(size=K)
+    r = rng.normal(size=N)
+    # low levels are well conditioned; the K largest-variance terms dominate: 1e-9 end to end
+    assert relerr(obg.matmul(terms, theta), obo.matmul(terms, theta)) < 1e-9
+    assert relerr(obg.tmatmul(terms, r), obo.tmatmul(terms, r)) < 1e-9
+    if N * K <= 200 * 100:
+        Gm = obg.getmat(terms)
+        assert relerr(Gm, obo.getmat(terms)) < 1e-9
+        # the reference's own identities on the GPU path
+        B = np.ones((N, K))
+        for k in range(8):
+            B *= obg.getbase(k + 1)[:, terms[:, k].astype(int)]
+        assert np.abs(Gm - B).sum() < 1e-8
+        assert np.abs(Gm @ theta - obg.matmul(terms, theta)).sum() < 1e-9
+        assert np.abs(Gm.T @ r - obg.tmatmul(terms, r)).sum() < 1e-8
+    # reported loop values follow modandbase.cpp:504-513
+    obg.nthreads = 8; obo.nthreads = 8
+    assert obg.chunksize == max(32, min(1 + 2048 // 8, N // 32 + 1))
+
+
+def test_squared_operators(gpu, oracle):
+    """sqmm / sqtmm / sqcolsums / sq*_gradhyp (modandbase.cpp:784-879) squared in shared memory."""
+    o = oracle_basis(oracle, 1000, 200)
+    omg, x, y, terms, rng = make_problem(gpu, 1000, 200)
+    obg = gpu.outerbase(omg, x)
+    a, r = rng.normal(size=200), rng.normal(size=1000)
+    ob = o["ob"]
+    assert relerr(obg.sqmm(terms, a), ob.sqmm(terms, a)) < 1e-9
+    assert relerr(obg.sqtmm(terms, r), ob.sqtmm(terms, r)) < 1e-9
+    assert relerr(obg.sqcolsums(terms), ob.sqcolsums(terms)) < 1e-9
+    assert relerr(obg.sqmm_gradhyp(terms, a), ob.sqmm_gradhyp(terms, a)) < 1e-8
+    assert relerr(obg.sqtmm_gradhyp(terms, r), ob.sqtmm_gradhyp(terms, r)) < 1e-8
+    assert relerr(obg.sqcolsums_gradhyp(terms), ob.sqcolsums_gradhyp(terms)) < 1e-8
+    assert relerr(obg.matmul_gradhyp(terms, a), ob.matmul_gradhyp(terms, a)) < 1e-8
+    assert relerr(obg.tmatmul_gradhyp(terms, r), ob.tmatmul_gradhyp(terms, r)) < 1e-8
+    R = np.asfortranarray(rng.normal(size=(1000, 3)))
+    assert relerr(obg.sqtmmm(terms, R), ob.sqtmmm(terms, R)) < 1e-9
+
+
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 127, 128, 129, 257])
+def test_ragged_row_counts(gpu, oracle, N):
+    o = oracle_basis(oracle, N, 40)
+    terms, rng = o["terms"], o["rng"]
+    a, r = rng.normal(size=40), rng.normal(size=N)
+    assert relerr(gpu.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
+    assert relerr(gpu.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+
+
+def test_degenerate_terms(gpu, oracle):
+    o = oracle_basis(oracle, 100, 30)
+    rng = o["rng"]
+    for terms in (o["terms"][:1], o["terms"][1:2], o["terms"][::-1][:7], np.asfortranarray(o["terms"][[3, 9, 17]])):
+        terms = np.asfortranarray(terms)
+        a, r = rng.normal(size=terms.shape[0]), rng.normal(size=100)
+        assert relerr(gpu.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
+        assert relerr(gpu.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+    with pytest.raises(ValueError):
+        bad = np.asfortranarray(o["terms"].copy()); bad[3, 2] = 1000
+        gpu.prodmm(bad, np.ones(30), o["bm"], o["bs"], o["kp"])
+
+
+def _lpdf_pair(lib, N, K, order="lik_first"):
+    om, x, y, terms, rng = make_problem(lib, N, K, covs=["mat25"] * 8, knots=[np.arange(0.001, 0.999, 0.05)] * 8)
+    logpr = lib.logpr_gauss(om, terms)
+    loglik = lib.loglik_gauss(om, terms, y, x)
+    vec = lib.lpdfvec(loglik, logpr) if order == "lik_first" else lib.lpdfvec(logpr, loglik)
+    return om, x, y, terms, rng, logpr, loglik, vec
+
+
+@pytest.mark.parametrize("N,K", [(200, 100), (10000, 100), (200, 1000)])
+def test_loglik_gauss_update_hessmult_diaghess(gpu, oracle, N, K):
+    """loglik_gauss (loglik_gauss.cpp:110-179) and lpdfvec (fit.cpp:323-361) as test-lpdf.R:20-35."""
+    O = _lpdf_pair(oracle, N, K)
+    G = _lpdf_pair(gpu, N, K)
+    rng = O[4]
+    coeff = rng.normal(size=K) / 100
+    g = rng.normal(size=K)
+    for (om, x, y, terms, _, logpr, loglik, vec) in (O, G):
+        for obj in (logpr, loglik, vec):
+            obj.compute_gradhyp = True; obj.compute_gradpara = True
+        loglik.updatepara([np.log(0.1)])
+        loglik.update(coeff)
+        vec.updatepara(vec.para)
+        vec.update(coeff)
+    lo, lg, vo, vg = O[6], G[6], O[7], G[7]
+    assert abs(lg.val - lo.val) <= 1e-8 * abs(lo.val)
+    assert relerr(lg.grad, lo.grad) < 1e-8
+    assert relerr(lg.gradhyp, lo.gradhyp) < 1e-7
+    assert relerr(lg.gradpara, lo.gradpara) < 1e-8
+    assert relerr(lg.yhat, lo.yhat) < 1e-9
+    assert relerr(lg.hessmult(g), lo.hessmult(g)) < 1e-8
+    assert relerr(lg.diaghess(), lo.diaghess()) < 1e-8
+    assert relerr(lg.diaghessgradhyp(), lo.diaghessgradhyp()) < 1e-7
+    assert relerr(lg.diaghessgradpara(), lo.diaghessgradpara()) < 1e-8
+    assert abs(vg.val - vo.val) <= 1e-8 * abs(vo.val)
+    assert relerr(vg.grad, vo.grad) < 1e-8
+    assert relerr(vg.gradhyp, vo.gradhyp) < 1e-7
+    assert relerr(vg.gradpara, vo.gradpara) < 1e-8
+    assert vg.paralpdf(vg.para + 0.1) == vo.paralpdf(vo.para + 0.1)
+
+
+@pytest.mark.parametrize("N,K,order", [(200, 100, "lik_first"), (10000, 100, "prior_first"), (10000, 1000, "prior_first")])
+def test_optcg_fit_parity(gpu, oracle, N, K, order):
+    """lpdf::optcg (fit.cpp:37-96), tol=0.001 maxepch=100 as .lpdfwrapper passes (R/outersupport.R:210-219):
+    coefficients and log-likelihood within 1e-8 relative (north_star)."""
+    O = _lpdf_pair(oracle, N, K, order)
+    G = _lpdf_pair(gpu, N, K, order)
+    for T in (O, G):
+        T[7].domarg = True
+        T[7].optcg(0.001, 100)
+    vo, vg = O[7], G[7]
+    assert vg.cg_iters == vo.cg_iters
+    assert abs(vg.val - vo.val) <= 1e-8 * abs(vo.val)
+    assert relerr(vg.coeff, vo.coeff) < 1e-8
+    assert relerr(vg.gradhyp, vo.gradhyp) < 1e-6
+    assert relerr(vg.gradpara, vo.gradpara) < 1e-7
+    # predictor(loglik): mean = Phi theta, var = (Phi o Phi) / totdiaghess + sd^2 (loglik_gauss.cpp:196-227)
+    po, pg = oracle.predictor(O[6]), gpu.predictor(G[6])
+    xn = np.asfortranarray(np.random.default_rng(5).uniform(size=(333, 8)))
+    po.update(xn); pg.update(xn)
+    assert relerr(pg.mean(), po.mean()) < 1e-8
+    assert relerr(pg.var(), po.var()) < 1e-8
+
+
+def test_full_size_properties(gpu):
+    """BASELINE config 3 shape (d=10, N=1M, K=2000): size-independent identities, no oracle."""
+    rng = np.random.default_rng(11)
+    d, N, K = 10, 1_000_000, 2000
+    x = np.asfortranarray(rng.uniform(size=(N, d)))
+    om = gpu.outermod()
+    om.setcovfs(["mat25pow"] * d)
+    q = np.linspace(0, 1, 40) * 40 / 41 + 0.5 / 41
+    om.setknot([np.quantile(x[:100000, l], q) for l in range(d)])
+    hyp = om.gethyp(); hyp[0::2] = np.linspace(-0.6, 0.4, d); om.updatehyp(hyp)
+    terms = om.selectterms(K)
+    ob = gpu.outerbase(om, x, dograd=False)
+    a1, a2 = rng.normal(size=K), rng.normal(size=K)
+    r = rng.normal(size=N)
+    y1, y2 = ob.matmul(terms, a1), ob.matmul(terms, a2)
+    # linearity
+    assert relerr(ob.matmul(terms, 2.0 * a1 - 3.0 * a2), 2.0 * y1 - 3.0 * y2) < 1e-12
+    # adjoint identity <Phi a, r> = <a, Phi^T r>
+    lhs, rhs = float(y1 @ r), float(a1 @ ob.tmatmul(terms, r))
+    assert abs(lhs - rhs) <= 1e-11 * (np.abs(y1) @ np.abs(r))
+    # row-block additivity of Phi^T (the multi-GPU reduction) and run-to-run determinism
+    t1 = ob.tmatmul(terms, r)
+    np.testing.assert_array_equal(t1, ob.tmatmul(terms, r))
+    half = N // 2
+    obA, obB = gpu.outerbase(om, x[:half], dograd=False), gpu.outerbase(om, x[half:], dograd=False)
+    assert relerr(obA.tmatmul(terms, r[:half]) + obB.tmatmul(terms, r[half:]), t1) < 1e-12
+    # squared operator against the explicit square on a row sample
+    s = ob.sqmm(terms, np.abs(a1))
+    assert np.all(s >= 0)
