@@ -83,52 +83,42 @@ struct PhiKParams {
   double* partial;
 };
 
+/* factor column -> registers.  tl = shared-space byte address of (tile base + this lane's first
+ * row); a column is 32*R*8 bytes.  Explicit ld.shared.v2.f64: one LDS.128 per row pair. */
 template <int R>
-__device__ __forceinline__ void load_factor(double (&f)[R], const double* bc, int lane) {
-  const double2 v0 = *reinterpret_cast<const double2*>(bc + 2 * lane);
-  f[0] = v0.x; f[1] = v0.y;
-  if constexpr (R == 4) {
-    const double2 v1 = *reinterpret_cast<const double2*>(bc + 64 + 2 * lane);
-    f[2] = v1.x; f[3] = v1.y;
-  }
+__device__ __forceinline__ void load_factor(double (&f)[R], uint32_t tl, uint32_t w) {
+  const uint32_t addr = tl + ((w & 0xFFFFu) * (uint32_t)(32 * R * sizeof(double)));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(f[0]), "=d"(f[1]) : "r"(addr));
+  if constexpr (R == 4) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(f[2]), "=d"(f[3]) : "r"(addr));
 }
 template <int R>
 __device__ __forceinline__ int tile_row(int lane, int r) { return (r >> 1) * 64 + 2 * lane + (r & 1); }
 
-/* register stack of SD slots; the index is warp-uniform, the switch keeps it in registers */
-template <int R, int SD>
-__device__ __forceinline__ void stk_get(double (&dst)[R], const double (&stk)[SD][R], uint32_t e) {
-#pragma unroll
-  for (int i = 0; i < SD; ++i)
-    if (e == (uint32_t)i) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) dst[r] = stk[i][r];
-    }
-}
-template <int R, int SD>
-__device__ __forceinline__ void stk_set(double (&stk)[SD][R], uint32_t e, const double (&src)[R]) {
-#pragma unroll
-  for (int i = 0; i < SD; ++i)
-    if (e == (uint32_t)i) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) stk[i][r] = src[r];
-    }
-}
+/* The register stack (SD slots of R doubles) is indexed by a warp-uniform depth.  Every
+ * access is a switch whose cases name fixed registers AND contain the consuming operation,
+ * so nothing is selected speculatively on the hot (leaf) path. */
+#define OB_CASES4(X) X(0) X(1) X(2) X(3)
+#define OB_CASES_HI(X) X(4) X(5) X(6) X(7)
 
-/* stage one row tile: nload columns of 32*R rows each, one bulk copy per column */
+/* stage one row tile: nload columns of 32*R rows each, one bulk copy per column.  Called by
+ * the producer warp only; UBLKCP takes uniform operands, so the copies are issued one by
+ * one whatever the lane mapping -- lane 0 does them all. */
 template <int R>
 __device__ __forceinline__ void issue_tile(const PhiKParams& p, double* T, uint64_t* bar, unsigned long long row0, int lane) {
   constexpr uint32_t colbytes = 32 * R * sizeof(double);
-  fence_proxy_async();
-  if (lane == 0) mbar_expect_tx(bar, colbytes * (uint32_t)p.nload);
+  if (lane == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(bar, colbytes * (uint32_t)p.nload);
+#pragma unroll 1
+    for (int c = 0; c < p.nload; ++c) bulk_g2s(T + (size_t)c * (32 * R), p.load_src[c] + row0, colbytes, bar);
+  }
   __syncwarp();
-  for (int c = lane; c < p.nload; c += 32) bulk_g2s(T + (size_t)c * (32 * R), p.load_src[c] + row0, colbytes, bar);
 }
 
 template <int R>
-__device__ __forceinline__ void transform_tile(const PhiKParams& p, double* T) {
+__device__ __forceinline__ void transform_tile(const PhiKParams& p, double* T, int nthreads) {
   constexpr int TR = 32 * R;
-  for (int idx = threadIdx.x; idx < p.ncol * TR; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < p.ncol * TR; idx += nthreads) {
     const int c = idx / TR, r = idx - c * TR;
     const int op = p.col_op[c];
     const double x = T[idx];
@@ -137,10 +127,13 @@ __device__ __forceinline__ void transform_tile(const PhiKParams& p, double* T) {
   }
 }
 
+constexpr int kComputeWarps = 16;                      /* = term groups of a program (ob_terms.hpp G) */
+constexpr int kPhiThreads = 32 * (kComputeWarps + 1);  /* + one producer warp issuing the bulk copies */
+
 /* ------------------------------------------------------------------ Phi a
- * One warp = one term group; lanes x R = the tile's rows.  Backward (Horner) stream. */
-template <int R, int SD>
-__global__ void __launch_bounds__(512, 1) phi_a_kernel(const PhiKParams p) {
+ * One compute warp = one term group; lanes x R = the tile's rows.  Backward (Horner) stream. */
+template <int R, int SD, bool PS>
+__global__ void __launch_bounds__(kPhiThreads, 1) phi_a_kernel(const PhiKParams p) {
   constexpr int TR = 32 * R;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -149,76 +142,90 @@ __global__ void __launch_bounds__(512, 1) phi_a_kernel(const PhiKParams p) {
   uint32_t* prog_sm = reinterpret_cast<uint32_t*>(smem + p.off_prog);
   double* part = reinterpret_cast<double*>(smem + p.off_part);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int G = blockDim.x >> 5;
+  const bool producer = warp == kComputeWarps;
 
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
-  for (int i = tid; i < p.nslots; i += blockDim.x) { const int t = p.slot_term[i]; a_sm[i] = t >= 0 ? p.a[t] : 0.0; }
-  if (p.prog_in_smem) for (int i = tid; i < p.nwords; i += blockDim.x) prog_sm[i] = p.prog[i];
+  for (int i = tid; i < p.nslots; i += kPhiThreads) { const int t = p.slot_term[i]; a_sm[i] = t >= 0 ? p.a[t] : 0.0; }
+  if (PS) for (int i = tid; i < p.nwords; i += kPhiThreads) prog_sm[i] = p.prog[i];
   __syncthreads();
-  const uint32_t* pw0 = (p.prog_in_smem ? prog_sm : p.prog) + p.prog_off[warp];
-  const int slot_hi = (int)p.slot_base[warp] + (int)p.slot_real[warp] - 1;
+  const uint32_t* pw0;
+  if (PS) pw0 = prog_sm + (producer ? 0 : p.prog_off[warp]);
+  else pw0 = p.prog + (producer ? 0 : p.prog_off[warp]);
+  const int slot_hi = producer ? 0 : (int)p.slot_base[warp] + (int)p.slot_real[warp] - 1;
 
   int tile = blockIdx.x;
-  if (warp == 0 && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
+  if (producer && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
   uint32_t phases = 0;
   double ssq_local = 0.0;
   for (int it = 0; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = (p.nbuf == 2) ? (it & 1) : 0;
     const int nxt = tile + gridDim.x;
-    if (p.nbuf == 2 && warp == 0 && nxt < p.ntiles)
+    if (p.nbuf == 2 && producer && nxt < p.ntiles)
       issue_tile<R>(p, tiles + (size_t)(buf ^ 1) * p.tile_doubles, &bars[buf ^ 1], (unsigned long long)nxt * TR, lane);
-    mbar_wait(&bars[buf], (phases >> buf) & 1u);
-    phases ^= (1u << buf);
     double* T = tiles + (size_t)buf * p.tile_doubles;
-    if (p.has_ops) { transform_tile<R>(p, T); __syncthreads(); }
+    if (!producer || p.has_ops) mbar_wait(&bars[buf], (phases >> buf) & 1u);
+    phases ^= (1u << buf);
+    if (p.has_ops) { transform_tile<R>(p, T, kPhiThreads); __syncthreads(); }
 
-    double cur[R], stk[SD][R];
+    if (!producer) {
+      double cur[R], stk[SD][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) cur[r] = 0.0;
-    const uint32_t* pw = pw0;
-    int slot = slot_hi;
-    for (;;) {
-      const uint32_t w = *pw++;
-      const uint32_t op = w >> 28;
-      if (op == B_END) break;
-      const double* bc = T + (size_t)(w & 0xFFFFu) * TR;
-      if (op == B_LEAF) {
-        double f[R];
-        load_factor<R>(f, bc, lane);
-        const double av = a_sm[slot--];
+      for (int r = 0; r < R; ++r) cur[r] = 0.0;
+      const uint32_t tl = smem_u32(T) + 16u * (uint32_t)lane;
+      const uint32_t* pw = pw0;
+      uint32_t w = pw[0], w1 = pw[1];
+      int slot = slot_hi;
+#pragma unroll 1
+      for (;;) {
+        const uint32_t w2 = pw[2]; /* two words ahead: the fetch never sits on the critical path */
+        ++pw;
+        if ((int32_t)w < 0) { /* B_LEAF: cur += B[col] * a[slot] */
+          double f[R];
+          load_factor<R>(f, tl, w);
+          const double av = a_sm[slot--];
 #pragma unroll
-        for (int r = 0; r < R; ++r) cur[r] = fma(f[r], av, cur[r]);
-      } else if (op == B_CLOSE_FRESH) {
-        double f[R];
-        load_factor<R>(f, bc, lane);
-        const double av = (w & (FLAG_HAS_A << 20)) ? a_sm[slot--] : 0.0;
+          for (int r = 0; r < R; ++r) cur[r] = fma(f[r], av, cur[r]);
+        } else {
+          const uint32_t op = w >> 28;
+          if (op == B_END) break;
+          const uint32_t e = (w >> 24) & 15u;
+          if (op == B_CLOSE_FRESH) {
+            double f[R];
+            load_factor<R>(f, tl, w);
+            const double av = (w & (FLAG_HAS_A << 20)) ? a_sm[slot--] : 0.0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) cur[r] = f[r] * (av + cur[r]);
-      } else if (op == B_CLOSE_LOAD) {
-        double f[R], base[R];
-        load_factor<R>(f, bc, lane);
-        const double av = (w & (FLAG_HAS_A << 20)) ? a_sm[slot--] : 0.0;
-        stk_get<R, SD>(base, stk, ((w >> 24) & 15u) - 1u);
+            for (int r = 0; r < R; ++r) cur[r] = f[r] * (av + cur[r]);
+          } else if (op == B_CLOSE_LOAD) {
+            double f[R];
+            load_factor<R>(f, tl, w);
+            const double av = (w & (FLAG_HAS_A << 20)) ? a_sm[slot--] : 0.0;
+#define X(i) case i + 1: _Pragma("unroll") for (int r = 0; r < R; ++r) cur[r] = fma(f[r], av + cur[r], stk[i][r]); break;
+            if constexpr (SD > 4) { switch (e) { OB_CASES4(X) OB_CASES_HI(X) default: break; } }
+            else { switch (e) { OB_CASES4(X) default: break; } }
+#undef X
+          } else if (op == B_SAVE) {
+#define X(i) case i: _Pragma("unroll") for (int r = 0; r < R; ++r) { stk[i][r] = cur[r]; cur[r] = 0.0; } break;
+            if constexpr (SD > 4) { switch (e) { OB_CASES4(X) OB_CASES_HI(X) default: break; } }
+            else { switch (e) { OB_CASES4(X) default: break; } }
+#undef X
+          } else { /* B_ROOT */
+            const double av = a_sm[slot--];
 #pragma unroll
-        for (int r = 0; r < R; ++r) cur[r] = fma(f[r], av + cur[r], base[r]);
-      } else if (op == B_SAVE) {
-        stk_set<R, SD>(stk, (w >> 24) & 15u, cur);
-#pragma unroll
-        for (int r = 0; r < R; ++r) cur[r] = 0.0;
-      } else { /* B_ROOT */
-        const double av = a_sm[slot--];
-#pragma unroll
-        for (int r = 0; r < R; ++r) cur[r] += av;
+            for (int r = 0; r < R; ++r) cur[r] += av;
+          }
+        }
+        w = w1; w1 = w2;
       }
-    }
 #pragma unroll
-    for (int r = 0; r < R; ++r) part[warp * TR + tile_row<R>(lane, r)] = cur[r];
+      for (int r = 0; r < R; ++r) part[warp * TR + tile_row<R>(lane, r)] = cur[r];
+    }
     __syncthreads();
     if (tid < TR) {
       const unsigned long long row = (unsigned long long)tile * TR + tid;
       if (row < p.N) {
         double s = 0.0;
-        for (int g = 0; g < G; ++g) s += part[g * TR + tid];
+#pragma unroll
+        for (int g = 0; g < kComputeWarps; ++g) s += part[g * TR + tid];
         double sc = p.scale[row];
         if (p.sq) sc = sc * sc;
         const double yv = s * sc;
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(512, 1) phi_a_kernel(const PhiKParams p) {
       }
     }
     __syncthreads();
-    if (p.nbuf == 1 && warp == 0 && nxt < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)nxt * TR, lane);
+    if (p.nbuf == 1 && producer && nxt < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)nxt * TR, lane);
   }
   if (p.mode == PHI_UPDATE) { /* deterministic per-CTA sum of squared standardised residuals */
     __syncthreads();
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(512, 1) phi_a_kernel(const PhiKParams p) {
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 /* e[0..7]: per-lane partial sums of 8 consecutive emits.  Returns, in every lane, the
- * full 32-lane sum of emit number ((lane>>2)&7) */
+ * full 32-lane sum of emit number 4*bit4(lane) + 2*bit3(lane) + bit2(lane) */
 __device__ __forceinline__ double butterfly8(double (&e)[8], int lane) {
   double h[4], q[2];
   const bool up16 = lane & 16;
@@ -278,11 +285,30 @@ __device__ __forceinline__ double butterfly8(double (&e)[8], int lane) {
   double v = keep + shfl_xor_d(send, 4);
   v += shfl_xor_d(v, 2);
   v += shfl_xor_d(v, 1);
-  return v; /* emit index = 4*bit4 + 2*bit3 + bit2 */
+  return v;
 }
 
-template <int R, int SD>
-__global__ void __launch_bounds__(512, 1) phi_t_kernel(const PhiKParams p) {
+/* cur = (from stack ? stk[d-1] : cur) * f ; optional save to stk[d] */
+#define OB_FWD_DESC()                                                                                   \
+  {                                                                                                     \
+    double f[R];                                                                                        \
+    load_factor<R>(f, tl, w);                                            \
+    if (op == F_DESC_STK) {                                                                             \
+      OB_SWITCH(d, OB_X_MULSTK)                                                                         \
+    } else {                                                                                            \
+      _Pragma("unroll") for (int r = 0; r < R; ++r) cur[r] *= f[r];                                     \
+    }                                                                                                   \
+    if (w & (FLAG_SAVE << 20)) { OB_SWITCH(d, OB_X_SAVE) }                                              \
+  }
+#define OB_X_MULSTK(i) case i + 1: _Pragma("unroll") for (int r = 0; r < R; ++r) cur[r] = stk[i][r] * f[r]; break;
+#define OB_X_SAVE(i) case i: _Pragma("unroll") for (int r = 0; r < R; ++r) stk[i][r] = cur[r]; break;
+#define OB_X_LOAD(i) case i: _Pragma("unroll") for (int r = 0; r < R; ++r) cur[r] = stk[i][r]; break;
+#define OB_SWITCH(sel, X)                                                       \
+  if constexpr (SD > 4) { switch (sel) { OB_CASES4(X) OB_CASES_HI(X) default: break; } } \
+  else { switch (sel) { OB_CASES4(X) default: break; } }
+
+template <int R, int SD, bool PS>
+__global__ void __launch_bounds__(kPhiThreads, 1) phi_t_kernel(const PhiKParams p) {
   constexpr int TR = 32 * R;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -290,99 +316,107 @@ __global__ void __launch_bounds__(512, 1) phi_t_kernel(const PhiKParams p) {
   double* acc_sm = reinterpret_cast<double*>(smem + p.off_vec);
   uint32_t* prog_sm = reinterpret_cast<uint32_t*>(smem + p.off_prog);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp == kComputeWarps;
 
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
-  for (int i = tid; i < p.nslots; i += blockDim.x) acc_sm[i] = 0.0;
-  if (p.prog_in_smem) for (int i = tid; i < p.nwords; i += blockDim.x) prog_sm[i] = p.prog[i];
+  for (int i = tid; i < p.nslots; i += kPhiThreads) acc_sm[i] = 0.0;
+  if (PS) for (int i = tid; i < p.nwords; i += kPhiThreads) prog_sm[i] = p.prog[i];
   __syncthreads();
-  const uint32_t* pw0 = (p.prog_in_smem ? prog_sm : p.prog) + p.prog_off[warp];
-  const int slot_lo = (int)p.slot_base[warp];
+  const uint32_t* pw0;
+  if (PS) pw0 = prog_sm + (producer ? 0 : p.prog_off[warp]);
+  else pw0 = p.prog + (producer ? 0 : p.prog_off[warp]);
+  const int slot_lo = producer ? 0 : (int)p.slot_base[warp];
   /* which of the 8 emits of a batch this lane owns after the butterfly, and whether it stores */
   const int my_emit = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const bool storer = (lane & 3) == 0;
 
   int tile = blockIdx.x;
-  if (warp == 0 && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
+  if (producer && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
   uint32_t phases = 0;
   for (int it = 0; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = (p.nbuf == 2) ? (it & 1) : 0;
     const int nxt = tile + gridDim.x;
-    if (p.nbuf == 2 && warp == 0 && nxt < p.ntiles)
+    if (p.nbuf == 2 && producer && nxt < p.ntiles)
       issue_tile<R>(p, tiles + (size_t)(buf ^ 1) * p.tile_doubles, &bars[buf ^ 1], (unsigned long long)nxt * TR, lane);
     /* b = basescale % a (linalg.cpp:312), zero beyond N */
     double cur[R], stk[SD][R];
+    if (!producer) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const unsigned long long row = (unsigned long long)tile * TR + tile_row<R>(lane, r);
-      double b = 0.0;
-      if (row < p.N) { double sc = p.scale[row]; if (p.sq) sc = sc * sc; b = sc * p.win[row]; }
-      stk[0][r] = b;
-      cur[r] = b;
+      for (int r = 0; r < R; ++r) {
+        const unsigned long long row = (unsigned long long)tile * TR + tile_row<R>(lane, r);
+        double b = 0.0;
+        if (row < p.N) { double sc = p.scale[row]; if (p.sq) sc = sc * sc; b = sc * p.win[row]; }
+        stk[0][r] = b;
+        cur[r] = b;
+      }
     }
-    mbar_wait(&bars[buf], (phases >> buf) & 1u);
-    phases ^= (1u << buf);
     double* T = tiles + (size_t)buf * p.tile_doubles;
-    if (p.has_ops) { transform_tile<R>(p, T); __syncthreads(); }
+    if (!producer || p.has_ops) mbar_wait(&bars[buf], (phases >> buf) & 1u);
+    phases ^= (1u << buf);
+    if (p.has_ops) { transform_tile<R>(p, T, kPhiThreads); __syncthreads(); }
 
-    const uint32_t* pw = pw0;
-    int slot = slot_lo;
-    bool done = false;
-    while (!done) {
-      double e[kEmitBatch];
+    if (!producer) {
+      const uint32_t tl = smem_u32(T) + 16u * (uint32_t)lane;
+      const uint32_t* pw = pw0;
+      uint32_t w = pw[0], w1 = pw[1];
+      int slot = slot_lo;
+      bool done = false;
+#pragma unroll 1
+      while (!done) {
+        double e[kEmitBatch];
 #pragma unroll
-      for (int i = 0; i < kEmitBatch; ++i) {
-        double acc = 0.0;
-        bool emitted = false;
-        while (!emitted) {
-          const uint32_t w = *pw;
-          const uint32_t op = w >> 28;
-          if (op == F_END) { done = true; break; }
+        for (int i = 0; i < kEmitBatch; ++i) {
+          /* words without output: pass nodes, LOADCUR.  END can only be met here, with i == 0
+           * (streams are padded to whole batches of emits). */
+#pragma unroll 1
+          while (!(w & (FLAG_EMIT << 20))) {
+            const uint32_t op = w >> 28;
+            if (op == F_END) { done = true; break; }
+            const uint32_t d = (w >> 24) & 15u;
+            if (op == F_LOADCUR) { OB_SWITCH(d, OB_X_LOAD) }
+            else OB_FWD_DESC()
+            const uint32_t w2 = pw[2];
+            ++pw; w = w1; w1 = w2;
+          }
+          if (done) break;
+          const uint32_t w2 = pw[2];
           ++pw;
-          const double* bc = T + (size_t)(w & 0xFFFFu) * TR;
-          if (op == F_LEAF) {
+          double acc;
+          if ((int32_t)w < 0) { /* F_LEAF: sum_r cur[r] * B[col][r] */
             double f[R];
-            load_factor<R>(f, bc, lane);
+            load_factor<R>(f, tl, w);
             acc = cur[0] * f[0];
 #pragma unroll
             for (int r = 1; r < R; ++r) acc = fma(cur[r], f[r], acc);
-          } else if (op == F_DESC_CUR || op == F_DESC_STK) {
-            double f[R];
-            load_factor<R>(f, bc, lane);
-            if (op == F_DESC_STK) stk_get<R, SD>(cur, stk, ((w >> 24) & 15u) - 1u);
+          } else {
+            const uint32_t op = w >> 28, d = (w >> 24) & 15u;
+            if (op == F_DESC_CUR || op == F_DESC_STK) {
+              OB_FWD_DESC()
+              acc = cur[0];
 #pragma unroll
-            for (int r = 0; r < R; ++r) cur[r] *= f[r];
-            if (w & (FLAG_SAVE << 20)) stk_set<R, SD>(stk, (w >> 24) & 15u, cur);
-            acc = cur[0];
+              for (int r = 1; r < R; ++r) acc += cur[r];
+            } else if (op == F_ROOT) {
+              acc = stk[0][0];
 #pragma unroll
-            for (int r = 1; r < R; ++r) acc += cur[r];
-          } else if (op == F_ROOT) {
-            acc = stk[0][0];
-#pragma unroll
-            for (int r = 1; r < R; ++r) acc += stk[0][r];
-          } else if (op == F_LOADCUR) {
-            stk_get<R, SD>(cur, stk, (w >> 24) & 15u);
-          } else { /* F_EMITZERO */
-            acc = 0.0;
+              for (int r = 1; r < R; ++r) acc += stk[0][r];
+            } else { /* F_EMITZERO */
+              acc = 0.0;
+            }
           }
-          emitted = (w & (FLAG_EMIT << 20)) != 0;
+          e[i] = acc;
+          w = w1; w1 = w2;
         }
-        e[i] = acc;
-        if (done) {
-#pragma unroll
-          for (int j = i; j < kEmitBatch; ++j) e[j] = 0.0;
-          break;
-        }
+        if (done) break;
+        const double tot = butterfly8(e, lane);
+        if (storer) acc_sm[slot + my_emit] += tot;
+        slot += kEmitBatch;
       }
-      if (done) break; /* streams are padded to whole batches, so nothing is pending here */
-      const double tot = butterfly8(e, lane);
-      if (storer) acc_sm[slot + my_emit] += tot;
-      slot += kEmitBatch;
     }
     __syncthreads();
-    if (p.nbuf == 1 && warp == 0 && nxt < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)nxt * TR, lane);
+    if (p.nbuf == 1 && producer && nxt < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)nxt * TR, lane);
   }
   __syncthreads();
-  for (int i = tid; i < p.nslots; i += blockDim.x) p.partial[(size_t)blockIdx.x * p.nslots + i] = acc_sm[i];
+  for (int i = tid; i < p.nslots; i += kPhiThreads) p.partial[(size_t)blockIdx.x * p.nslots + i] = acc_sm[i];
 }
 
 /* out[term(slot)] = sum over CTAs, fixed order */
@@ -773,6 +807,7 @@ struct PhiGeom {
 
 /* choose rows per lane / buffering so that the staged tile fits the 227 KB of the SM */
 static PhiGeom phi_geometry(const Ctx& c, const DevProgram& pr, const ColTable& ct, bool is_a, u64 N) {
+  const bool deep = (is_a ? pr.host.bwd_stack : pr.host.fwd_stack) > 4; /* R=4 with 8 stack slots spills */
   const size_t nwords = is_a ? pr.host.bwd.size() : pr.host.fwd.size();
   const size_t vec_bytes = ((pr.host.nslots() * sizeof(double) + 127) / 128) * 128;
   const int Rs[2] = {4, 2};
@@ -780,7 +815,7 @@ static PhiGeom phi_geometry(const Ctx& c, const DevProgram& pr, const ColTable& 
     for (int nbuf = 2; nbuf >= 1; --nbuf)
       for (int ri = 0; ri < 2; ++ri) {
         const int R = Rs[ri], TR = 32 * R;
-        if (R == 4 && N <= (u64)c.sms * 64) continue; /* small inputs: finer tiles fill more SMs */
+        if (R == 4 && (deep || N <= (u64)c.sms * 64)) continue; /* small inputs: finer tiles fill more SMs */
         PhiGeom g;
         g.R = R; g.nbuf = nbuf; g.G = pr.host.G;
         g.off_tile = 128;
@@ -791,7 +826,7 @@ static PhiGeom phi_geometry(const Ctx& c, const DevProgram& pr, const ColTable& 
         g.prog_in_smem = (pass == 0);
         if (g.prog_in_smem) off += ((nwords * 4 + 127) / 128) * 128;
         g.off_part = (unsigned)off;
-        if (is_a) off += (size_t)g.G * TR * sizeof(double);
+        if (is_a) off += (size_t)kComputeWarps * TR * sizeof(double);
         g.smem = off;
         if (g.smem <= c.smem_optin) return g;
       }
@@ -839,10 +874,12 @@ void launch_phi_a(Ctx& c, const PhiPlan& pl, const PhiAArgs& a, Workspace& ws, i
   p.a = a.a; p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
   const int grid = phi_grid(c, pl.N, 32 * g.R);
   if (a.mode == PHI_UPDATE) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
-#define OB_LAUNCH_A(RR, SS) { set_smem(phi_a_kernel<RR, SS>, g.smem); phi_a_kernel<RR, SS><<<grid, 32 * g.G, g.smem, c.stream>>>(p); }
+#define OB_LAUNCH_A(RR, SS, PP) { set_smem(phi_a_kernel<RR, SS, PP>, g.smem); phi_a_kernel<RR, SS, PP><<<grid, kPhiThreads, g.smem, c.stream>>>(p); }
+#define OB_LAUNCH_A2(RR, SS) { if (g.prog_in_smem) OB_LAUNCH_A(RR, SS, true) else OB_LAUNCH_A(RR, SS, false) }
   const int sd = pr.host.bwd_stack;
-  if (g.R == 4) { if (sd <= 4) OB_LAUNCH_A(4, 4) else OB_LAUNCH_A(4, 8) }
-  else { if (sd <= 4) OB_LAUNCH_A(2, 4) else OB_LAUNCH_A(2, 8) }
+  if (g.R == 4) { if (sd <= 4) OB_LAUNCH_A2(4, 4) else OB_LAUNCH_A2(4, 8) }
+  else { if (sd <= 4) OB_LAUNCH_A2(2, 4) else OB_LAUNCH_A2(2, 8) }
+#undef OB_LAUNCH_A2
 #undef OB_LAUNCH_A
   check_launch(c, "phi_a_kernel");
   if (grid_out) *grid_out = grid;
@@ -868,10 +905,12 @@ void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Works
   const int grid = phi_grid(c, pl.N, 32 * g.R);
   p.win = w;
   p.partial = ws.partial.ensure((size_t)grid * p.nslots);
-#define OB_LAUNCH_T(RR, SS) { set_smem(phi_t_kernel<RR, SS>, g.smem); phi_t_kernel<RR, SS><<<grid, 32 * g.G, g.smem, c.stream>>>(p); }
+#define OB_LAUNCH_T(RR, SS, PP) { set_smem(phi_t_kernel<RR, SS, PP>, g.smem); phi_t_kernel<RR, SS, PP><<<grid, kPhiThreads, g.smem, c.stream>>>(p); }
+#define OB_LAUNCH_T2(RR, SS) { if (g.prog_in_smem) OB_LAUNCH_T(RR, SS, true) else OB_LAUNCH_T(RR, SS, false) }
   const int sd = pr.host.fwd_stack;
-  if (g.R == 4) { if (sd <= 4) OB_LAUNCH_T(4, 4) else OB_LAUNCH_T(4, 8) }
-  else { if (sd <= 4) OB_LAUNCH_T(2, 4) else OB_LAUNCH_T(2, 8) }
+  if (g.R == 4) { if (sd <= 4) OB_LAUNCH_T2(4, 4) else OB_LAUNCH_T2(4, 8) }
+  else { if (sd <= 4) OB_LAUNCH_T2(2, 4) else OB_LAUNCH_T2(2, 8) }
+#undef OB_LAUNCH_T2
 #undef OB_LAUNCH_T
   check_launch(c, "phi_t_kernel");
   phi_t_reduce_kernel<<<(p.nslots + 127) / 128, 128, 0, c.stream>>>(p.partial, grid, p.nslots, pr.slot_term.p, out);

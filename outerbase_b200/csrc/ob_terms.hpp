@@ -38,11 +38,13 @@ using u64 = uint64_t;
 
 constexpr int kMaxDepth = 8;      /* register stack slots of the interpreter */
 constexpr int kEmitBatch = 8;     /* forward emits are padded to a multiple of this per warp */
+constexpr int kPrefetch = 2;      /* END words appended to every stream: the interpreters read two words ahead */
 
 /* forward (Phi^T) opcodes */
-enum : uint32_t { F_END = 0, F_LEAF = 1, F_DESC_CUR = 2, F_DESC_STK = 3, F_ROOT = 4, F_LOADCUR = 5, F_EMITZERO = 6 };
+/* bit 31 of a word (op >= 8) marks a LEAF: the interpreters test it first (~75% of all words) */
+enum : uint32_t { F_END = 0, F_LEAF = 8, F_DESC_CUR = 2, F_DESC_STK = 3, F_ROOT = 4, F_LOADCUR = 5, F_EMITZERO = 6 };
 /* backward (Phi a) opcodes */
-enum : uint32_t { B_END = 0, B_LEAF = 1, B_CLOSE_FRESH = 2, B_CLOSE_LOAD = 3, B_SAVE = 4, B_ROOT = 5 };
+enum : uint32_t { B_END = 0, B_LEAF = 8, B_CLOSE_FRESH = 2, B_CLOSE_LOAD = 3, B_SAVE = 4, B_ROOT = 5 };
 constexpr uint32_t FLAG_EMIT = 1, FLAG_SAVE = 2, FLAG_HAS_A = 1;
 inline uint32_t mkword(uint32_t op, uint32_t depth, uint32_t flags, uint32_t col) {
   return (op << 28) | ((depth & 15u) << 24) | ((flags & 15u) << 20) | (col & 0xFFFFu);
@@ -259,7 +261,7 @@ inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) 
     }
     const uint32_t nreal = (uint32_t)slots.size();
     while (slots.size() % kEmitBatch) { fw.push_back(mkword(F_EMITZERO, 0, FLAG_EMIT, 0)); slots.push_back(-1); }
-    fw.push_back(mkword(F_END, 0, 0, 0));
+    for (int i = 0; i <= kPrefetch; ++i) fw.push_back(mkword(F_END, 0, 0, 0));
     /* backward: exact reverse node order of the forward stream */
     struct Bwd {
       const std::vector<Node>& nd; std::vector<uint32_t>& bw;
@@ -302,7 +304,7 @@ inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) 
           for (int v = nd[s].parent; v > 0; v = nd[v].parent) Bk.close(v, false);
       }
     }
-    bw.push_back(mkword(B_END, 0, 0, 0));
+    for (int i = 0; i <= kPrefetch; ++i) bw.push_back(mkword(B_END, 0, 0, 0));
     P.fwd_off[g + 1] = P.fwd_off[g] + (uint32_t)fw.size();
     P.bwd_off[g + 1] = P.bwd_off[g] + (uint32_t)bw.size();
     P.fwd.insert(P.fwd.end(), fw.begin(), fw.end());

@@ -119,10 +119,22 @@ def test_basis_build(gpu, oracle, covs):
         err = np.abs(bg[:, kp[l]:kp[l + 1]] - bo[:, kp[l]:kp[l + 1]])
         # a few units of m*eps times the magnitude of the summed terms (+ the same for the divisor)
         assert np.all(err <= 8 * m * eps * (bound + np.abs(bo[:, kp[l]:kp[l + 1]]) * bound[:, [0]])), f"dim {l}"
-    # gradient blocks: same criterion, looser constant; checked through their effect below
+    # gradient blocks Rt = covg.rot + cov.rotg, divided by P0 (modandbase.cpp:315-325): same criterion
     go, gg = obo.real("basemat_gradhyp"), obg.real("basemat_gradhyp")
-    used = np.abs(go) > 0
-    assert np.median(np.abs(gg - go)[used] / np.abs(go)[used]) < 1e-9
+    rotg, gest, hypst = omo.real("rotmat_gradhyp"), omo.index("gest"), omo.index("hypst")
+    for l in range(8):
+        m = int(kp[l + 1] - kp[l])
+        hl = hyp[hypst[l]:hypst[l + 1]]
+        kn = omo.real("knotpt")[kp[l]:kp[l + 1]]
+        C = np.abs(oracle.covf_cov(names[l], hl, x[:, l], kn))
+        Cg = np.abs(oracle.covf_cov_gradhyp(names[l], hl, x[:, l], kn))
+        p0 = np.abs(so[:, [l]])
+        rel0 = (C @ np.abs(rot[:m, kp[l]])[:, None]) / p0  # relative forward error scale of the divisor
+        for j, h in enumerate(range(hypst[l], hypst[l + 1])):
+            blk = slice(gest[h], gest[h] + m)
+            bound = (Cg[:, :, j] @ np.abs(rot[:m, kp[l]:kp[l + 1]]) + C @ np.abs(rotg[:m, blk])) / p0
+            err = np.abs(gg[:, blk] - go[:, blk])
+            assert np.all(err <= 8 * m * eps * (bound + np.abs(go[:, blk]) * rel0)), f"dim {l} hyper {h}"
     # getbase = un-normalised P_l (modandbase.cpp:634-639)
     assert relerr(obg.getbase(3)[:, :6], obo.getbase(3)[:, :6]) < 1e-9
 
