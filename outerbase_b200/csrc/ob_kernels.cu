@@ -257,37 +257,26 @@ __global__ void __launch_bounds__(kPhiThreads, 1) phi_a_kernel(const PhiKParams 
 
 /* ------------------------------------------------------------------ Phi^T r
  * Forward (top-down) stream; per-term row sums are reduced across the warp with an
- * 8-term butterfly (one 64-bit exchange halves eight sums at once) and accumulated
- * into CTA-private shared-memory slots; every slot belongs to exactly one warp. */
+ * incremental 8-term butterfly and accumulated into CTA-private shared-memory slots;
+ * every slot belongs to exactly one warp. */
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-/* e[0..7]: per-lane partial sums of 8 consecutive emits.  Returns, in every lane, the
- * full 32-lane sum of emit number 4*bit4(lane) + 2*bit3(lane) + bit2(lane) */
-__device__ __forceinline__ double butterfly8(double (&e)[8], int lane) {
-  double h[4], q[2];
-  const bool up16 = lane & 16;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { /* lanes with bit4 keep emits 4..7 */
-    const double keep = up16 ? e[i + 4] : e[i];
-    const double send = up16 ? e[i] : e[i + 4];
-    h[i] = keep + shfl_xor_d(send, 16);
-  }
-  const bool up8 = lane & 8;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const double keep = up8 ? h[i + 2] : h[i];
-    const double send = up8 ? h[i] : h[i + 2];
-    q[i] = keep + shfl_xor_d(send, 8);
-  }
-  const bool up4 = lane & 4;
-  const double keep = up4 ? q[1] : q[0];
-  const double send = up4 ? q[0] : q[1];
-  double v = keep + shfl_xor_d(send, 4);
-  v += shfl_xor_d(v, 2);
-  v += shfl_xor_d(v, 1);
-  return v;
+/* Incremental 8-way butterfly.  Row sums of consecutive emits are paired as they arrive: two
+ * pending sums are merged with ONE 64-bit exchange (each half of the lanes keeps one of them),
+ * so eight emits cost 4+2+1 merging exchanges plus two plain ones instead of 8 x 5.  The
+ * pending registers form a binary counter on the warp-uniform emit count, which keeps the
+ * interpreter a single compact loop (no unrolling, no register indexing).
+ * After the 8th emit every lane holds the full 32-lane sum of emit
+ *   bit4(lane) + 2*bit3(lane) + 4*bit2(lane)   of the batch. */
+struct EmitState {
+  double p1, p2, p3;
+  uint32_t cnt;
+};
+__device__ __forceinline__ double merge_xor(double first, double second, bool upper, int m) {
+  const double keep = upper ? second : first;
+  const double send = upper ? first : second;
+  return keep + shfl_xor_d(send, m);
 }
-
 /* cur = (from stack ? stk[d-1] : cur) * f ; optional save to stk[d] */
 #define OB_FWD_DESC()                                                                                   \
   {                                                                                                     \
@@ -327,8 +316,9 @@ __global__ void __launch_bounds__(kPhiThreads, 1) phi_t_kernel(const PhiKParams 
   else pw0 = p.prog + (producer ? 0 : p.prog_off[warp]);
   const int slot_lo = producer ? 0 : (int)p.slot_base[warp];
   /* which of the 8 emits of a batch this lane owns after the butterfly, and whether it stores */
-  const int my_emit = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const int my_emit = ((lane >> 4) & 1) + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) * 4;
   const bool storer = (lane & 3) == 0;
+  const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
 
   int tile = blockIdx.x;
   if (producer && tile < p.ntiles) issue_tile<R>(p, tiles, &bars[0], (unsigned long long)tile * TR, lane);
@@ -360,56 +350,57 @@ __global__ void __launch_bounds__(kPhiThreads, 1) phi_t_kernel(const PhiKParams 
       const uint32_t* pw = pw0;
       uint32_t w = pw[0], w1 = pw[1];
       int slot = slot_lo;
-      bool done = false;
+      EmitState es;
+      es.p1 = es.p2 = es.p3 = 0.0;
+      es.cnt = 0;
 #pragma unroll 1
-      while (!done) {
-        double e[kEmitBatch];
+      for (;;) {
+        const uint32_t w2 = pw[2];
+        ++pw;
+        double acc;
+        if ((int32_t)w < 0) { /* F_LEAF: sum_r cur[r] * B[col][r] */
+          double f[R];
+          load_factor<R>(f, tl, w);
+          acc = cur[0] * f[0];
 #pragma unroll
-        for (int i = 0; i < kEmitBatch; ++i) {
-          /* words without output: pass nodes, LOADCUR.  END can only be met here, with i == 0
-           * (streams are padded to whole batches of emits). */
-#pragma unroll 1
-          while (!(w & (FLAG_EMIT << 20))) {
-            const uint32_t op = w >> 28;
-            if (op == F_END) { done = true; break; }
-            const uint32_t d = (w >> 24) & 15u;
-            if (op == F_LOADCUR) { OB_SWITCH(d, OB_X_LOAD) }
-            else OB_FWD_DESC()
-            const uint32_t w2 = pw[2];
-            ++pw; w = w1; w1 = w2;
+          for (int r = 1; r < R; ++r) acc = fma(cur[r], f[r], acc);
+        } else {
+          const uint32_t op = w >> 28, d = (w >> 24) & 15u;
+          if (op == F_END) break;
+          acc = 0.0; /* F_EMITZERO */
+          if (op == F_DESC_CUR || op == F_DESC_STK) {
+            OB_FWD_DESC()
+            acc = cur[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc += cur[r];
+          } else if (op == F_ROOT) {
+            acc = stk[0][0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) acc += stk[0][r];
+          } else if (op == F_LOADCUR) {
+            OB_SWITCH(d, OB_X_LOAD)
           }
-          if (done) break;
-          const uint32_t w2 = pw[2];
-          ++pw;
-          double acc;
-          if ((int32_t)w < 0) { /* F_LEAF: sum_r cur[r] * B[col][r] */
-            double f[R];
-            load_factor<R>(f, tl, w);
-            acc = cur[0] * f[0];
-#pragma unroll
-            for (int r = 1; r < R; ++r) acc = fma(cur[r], f[r], acc);
-          } else {
-            const uint32_t op = w >> 28, d = (w >> 24) & 15u;
-            if (op == F_DESC_CUR || op == F_DESC_STK) {
-              OB_FWD_DESC()
-              acc = cur[0];
-#pragma unroll
-              for (int r = 1; r < R; ++r) acc += cur[r];
-            } else if (op == F_ROOT) {
-              acc = stk[0][0];
-#pragma unroll
-              for (int r = 1; r < R; ++r) acc += stk[0][r];
-            } else { /* F_EMITZERO */
-              acc = 0.0;
+        }
+        if (w & (FLAG_EMIT << 20)) {
+          const uint32_t c = es.cnt++;
+          if (!(c & 1u)) es.p1 = acc;
+          else {
+            const double h = merge_xor(es.p1, acc, up16, 16);
+            if (!(c & 2u)) es.p2 = h;
+            else {
+              const double q = merge_xor(es.p2, h, up8, 8);
+              if (!(c & 4u)) es.p3 = q;
+              else {
+                double v = merge_xor(es.p3, q, up4, 4);
+                v += shfl_xor_d(v, 2);
+                v += shfl_xor_d(v, 1);
+                if (storer) acc_sm[slot + my_emit] += v;
+                slot += kEmitBatch;
+              }
             }
           }
-          e[i] = acc;
-          w = w1; w1 = w2;
         }
-        if (done) break;
-        const double tot = butterfly8(e, lane);
-        if (storer) acc_sm[slot + my_emit] += tot;
-        slot += kEmitBatch;
+        w = w1; w1 = w2;
       }
     }
     __syncthreads();
