@@ -1,0 +1,104 @@
+"""Multi-rank worker: rows sharded over ranks, Phi^T-type results combined by allreduce.
+
+backend gloo  -> CPU: each rank runs the ORACLE on its row block and the partial sums are combined
+                 with torch.distributed (tests the sharding arithmetic and bench.py's row generator);
+backend nccl  -> GPU: each rank runs the PRODUCT on its own B200, allreduce inside the C library
+                 (ncclAllReduce on the library's stream); compared with the single-rank oracle.
+Launched by tests/test_multirank.py (gloo, world 2) and by `torchrun` on a multi-GPU box.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests"))
+from conftest import make_problem, relerr  # noqa: E402
+from outerbase_b200.binding import Library  # noqa: E402
+import bench  # noqa: E402
+
+
+def main():
+    backend = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    oracle = Library(REPO / "oracle" / "_build" / "libob_oracle.so", "orc_")
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import outerbase_b200 as obp
+        lib = obp.lib(local)
+        box = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        lib.comm_init(world, rank, box[0])
+        assert lib.comm_info() == (world, rank)
+    else:
+        dist.init_process_group("gloo")
+        lib = oracle
+
+    # bench.py's row generator gives the same rows for any sharding
+    full = bench.synth_rows(0, 5000, 4)
+    lo, hi = (5000 * rank) // world, (5000 * (rank + 1)) // world
+    np.testing.assert_array_equal(bench.synth_rows(lo, hi, 4), full[lo:hi])
+
+    N, K = 6001, 300
+    omr, x, y, terms, rng = make_problem(oracle, N, K, covs=["mat25"] * 8, knots=[np.arange(0.001, 0.999, 0.05)] * 8)
+    lo, hi = (N * rank) // world, (N * (rank + 1)) // world
+    om, *_ = make_problem(lib, N, K, covs=["mat25"] * 8, knots=[np.arange(0.001, 0.999, 0.05)] * 8)
+    a, r = rng.normal(size=K) / 50, rng.normal(size=N)
+    ref_ob = oracle.outerbase(omr, x)
+    ob = lib.outerbase(om, x[lo:hi])
+    # Phi a: row-local, no communication
+    assert relerr(ob.matmul(terms, a), ref_ob.matmul(terms, a)[lo:hi]) < 1e-9
+    # Phi^T r: partial sums over the rank's rows, summed over ranks
+    part = ob.tmatmul(terms, r[lo:hi])
+    if backend == "gloo":
+        t = torch.from_numpy(part.copy()); dist.all_reduce(t); part = t.numpy()
+    assert relerr(part, ref_ob.tmatmul(terms, r)) < 1e-9
+
+    # loglik_gauss / optcg on sharded rows
+    ref = oracle.lpdfvec(oracle.logpr_gauss(omr, terms), oracle.loglik_gauss(omr, terms, y, x))
+    ref.optcg(0.001, 100)
+    if backend == "nccl":
+        loglik = lib.loglik_gauss(om, terms, y[lo:hi], x[lo:hi])
+        vec = lib.lpdfvec(lib.logpr_gauss(om, terms), loglik)
+        # default noise scale log(0.01 var(y)) is computed over ALL ranks' rows inside the library
+        assert abs(vec.para[1] - ref.para[1]) < 1e-12 * abs(ref.para[1]), (vec.para, ref.para)
+        vec.updatepara(ref.para)
+        vec.optcg(0.001, 100)
+        assert vec.cg_iters == ref.cg_iters, (vec.cg_iters, ref.cg_iters)
+        assert relerr(vec.coeff, ref.coeff) < 1e-8
+        assert abs(vec.val - ref.val) <= 1e-8 * abs(ref.val)
+        assert relerr(vec.gradhyp, ref.gradhyp) < 1e-6
+        # every rank holds bit-identical results (allreduce gives all ranks the same bits)
+        t = torch.from_numpy(vec.coeff.copy()).cuda()
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        assert torch.equal(tmax, tmin)
+    else:
+        # the reduction loglik_gauss::update needs: grad (K) | ssq | row count, one allreduce
+        lk = oracle.loglik_gauss(omr, terms, y[lo:hi], x[lo:hi])
+        lk.updatepara(ref.para[1:2])
+        lk.compute_gradpara = True
+        lk.update(ref.coeff)
+        sd = np.exp(ref.para[1])
+        buf = torch.from_numpy(np.concatenate([lk.grad, [lk.gradpara[0] + (hi - lo)], [hi - lo]]))
+        dist.all_reduce(buf)
+        full_lk = oracle.loglik_gauss(omr, terms, y, x)
+        full_lk.updatepara(ref.para[1:2]); full_lk.compute_gradpara = True; full_lk.update(ref.coeff)
+        assert relerr(buf[:K].numpy(), full_lk.grad) < 1e-11
+        ssq, n = float(buf[K]), float(buf[K + 1])
+        assert n == N
+        assert abs((-0.5 * ssq - n * np.log(sd)) - full_lk.val) <= 1e-11 * abs(full_lk.val)
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu_worker[{backend}] world={world} OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
