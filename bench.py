@@ -222,7 +222,7 @@ def main():
     dev = torch.device("cuda", local)
     a_d = torch.from_numpy(a_h).to(dev)
     r_d = torch.from_numpy(r_h).to(dev)
-    yhat_d = torch.empty(((nloc + 127) // 128) * 128, dtype=torch.float64, device=dev)
+    yhat_d = torch.empty(((nloc + 255) // 256) * 256, dtype=torch.float64, device=dev)
     g_d = torch.empty(K_TERMS, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 

@@ -209,8 +209,8 @@ int ob_outerbase_set_terms(ob_outerbase* ob, const uint64_t* terms, uint64_t K) 
   obe::OuterBase& b = *ob->ob;
   b.cur_terms.assign(terms, terms + K * b.d);
   b.cur_K = K;
-  b.program(b.cur_terms.data(), K, -1);
-  b.coltable(b.program(b.cur_terms.data(), K, -1), 0, -1);
+  b.coltable(b.program(b.cur_terms.data(), K, -1, 0), 0, -1);
+  b.coltable(b.program(b.cur_terms.data(), K, -1, 1), 0, -1);
   OB_CATCH
 }
 int ob_outerbase_mm_dev(ob_outerbase* ob, int sq, const double* a_dev, double* out_dev) {

@@ -28,7 +28,8 @@ using obd::DevBuf;
 using obh::OuterMod;
 using u64 = uint64_t;
 
-inline u64 pad128(u64 n) { return ((n + 127) / 128) * 128; }
+/* leading dimension of every N-row device matrix: whole 256-row tiles, pad rows zero */
+inline u64 pad128(u64 n) { return ((n + 255) / 256) * 256; }
 
 inline bool all_finite(const std::vector<double>& v) {
   for (double x : v) if (!std::isfinite(x)) return false;
@@ -49,7 +50,7 @@ struct OuterBase {
   obd::Workspace ws;
   DevBuf<double> tmpK, tmpN, tmpN2, tmpP;
 
-  struct ProgEntry { std::vector<u64> terms; u64 K; int aug; std::unique_ptr<obd::DevProgram> prog; };
+  struct ProgEntry { std::vector<u64> terms; u64 K; int aug; int G; int cap; std::unique_ptr<obd::DevProgram> prog; };
   std::list<ProgEntry> programs;
   struct ColEntry { const obd::DevProgram* prog; int sq; int h; std::unique_ptr<obd::ColTable> ct; };
   std::list<ColEntry> coltables;
@@ -130,18 +131,28 @@ struct OuterBase {
     om_version = om->version;
   }
 
-  obd::DevProgram* program(const u64* terms, u64 K, int aug) {
+  /* the program a Phi kernel runs.  dir 0 = Phi a, 1 = Phi^T.  Measured at C3 (profiles/): Phi a is
+   * fastest on the shared-memory kernel (16 term groups), Phi^T on the TMEM kernel (4 term groups);
+   * OB_PHI=v1|v2 forces one generation for both. */
+  obd::DevProgram* program(const u64* terms, u64 K, int aug, int dir = 0) {
+    if (obd::tmem_kernels_enabled(dir)) {
+      obd::DevProgram* p4 = program_g(terms, K, aug, 4, 512 / (2 * obd::tmem_rows_per_lane(ctx, N)));
+      if (obd::tmem_eligible(p4->host) && obd::tmem_fits(ctx, *p4, (int)p4->host.cols.size(), N)) return p4;
+    }
+    return program_g(terms, K, aug, 16, 0);
+  }
+  obd::DevProgram* program_g(const u64* terms, u64 K, int aug, int G, int cap) {
     for (auto it = programs.begin(); it != programs.end(); ++it)
-      if (it->K == K && it->aug == aug && std::memcmp(it->terms.data(), terms, K * d * sizeof(u64)) == 0) {
+      if (it->K == K && it->aug == aug && it->G == G && it->cap == cap && std::memcmp(it->terms.data(), terms, K * d * sizeof(u64)) == 0) {
         programs.splice(programs.begin(), programs, it);
         return programs.front().prog.get();
       }
     check_terms(terms, K);
     ProgEntry e;
     e.terms.assign(terms, terms + K * d);
-    e.K = K; e.aug = aug;
+    e.K = K; e.aug = aug; e.G = G; e.cap = cap;
     e.prog.reset(new obd::DevProgram());
-    e.prog->host = obt::compile(terms, K, d, 16, aug);
+    e.prog->host = obt::compile(terms, K, d, G, aug, cap);
     e.prog->upload(ctx.stream);
     ctx.sync();
     programs.push_front(std::move(e));
@@ -198,7 +209,7 @@ struct OuterBase {
     obd::launch_phi_a(ctx, plan(program(terms, K, -1), sq, -1), a, ws, nullptr);
   }
   void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true) {
-    obd::launch_phi_t(ctx, plan(program(terms, K, -1), sq, -1), w_dev, out_dev, ws);
+    obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
     if (reduce_ranks) ctx.allreduce_sum(out_dev, K);
   }
   /* prodmmge_: outge column h = augmented-program product (ob_terms.hpp) */
@@ -212,9 +223,9 @@ struct OuterBase {
   }
   void tmm_ge_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev /* K*(1+H): out | outge */) {
     if (!dograd) throw std::logic_error("outerbase was built without gradients");
-    obd::launch_phi_t(ctx, plan(program(terms, K, -1), sq, -1), w_dev, out_dev, ws);
+    obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
     for (u64 h = 0; h < H; ++h)
-      obd::launch_phi_t(ctx, plan(program(terms, K, (int)hypmatch[h]), sq, (int)h), w_dev, out_dev + (1 + h) * K, ws);
+      obd::launch_phi_t(ctx, plan(program(terms, K, (int)hypmatch[h], 1), sq, (int)h), w_dev, out_dev + (1 + h) * K, ws);
     ctx.allreduce_sum(out_dev, K * (1 + H));
   }
 
@@ -520,7 +531,7 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     OB_CUDA(cudaMemsetAsync(red.p, 0, (K + 1 + H) * sizeof(double), ctx.stream));
     if (grid > 0) obd::launch_sum_partials(ctx, ob.ws.ssq.p, grid, red.p + K);
     const bool dohyp = compute_grad && compute_gradhyp;
-    if (compute_grad) obd::launch_phi_t(ctx, ob.plan(pr, 0, -1), w.p, red.p, ob.ws);
+    if (compute_grad) obd::launch_phi_t(ctx, ob.plan(ob.program(terms.data(), K, -1, 1), 0, -1), w.p, red.p, ob.ws);
     if (dohyp) { /* gradhyp = residtemp^T * yhatge, :127 -- yhatge column h is never stored */
       gebuf.ensure(ob.ld + 4 * ctx.sms);
       for (u64 h = 0; h < H; ++h) {
@@ -550,7 +561,7 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     a.a = kbuf.p; a.w = w.p; a.sd = obssd; a.mode = obd::PHI_HESS;
     obd::launch_phi_a(ctx, ob.plan(pr, 0, -1), a, ob.ws, nullptr);
     red.ensure(K);
-    obd::launch_phi_t(ctx, ob.plan(pr, 0, -1), w.p, red.p, ob.ws);
+    obd::launch_phi_t(ctx, ob.plan(ob.program(terms.data(), K, -1, 1), 0, -1), w.p, red.p, ob.ws);
     ctx.allreduce_sum(red.p, K);
     std::vector<double> o(K);
     ob.d2h(o.data(), red.p, K);

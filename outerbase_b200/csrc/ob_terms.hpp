@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <map>
+#include <numeric>
 #include <stdexcept>
 #include <vector>
 
@@ -37,8 +38,8 @@ namespace obt {
 using u64 = uint64_t;
 
 constexpr int kMaxDepth = 8;      /* register stack slots of the interpreter */
-constexpr int kEmitBatch = 8;     /* forward emits are padded to a multiple of this per warp */
-constexpr int kPrefetch = 2;      /* END words appended to every stream: the interpreters read two words ahead */
+constexpr int kEmitBatch = 16;    /* forward emits are padded to a multiple of this per warp */
+constexpr int kPrefetch = 8;      /* END words appended to every stream: the interpreters read up to seven words ahead */
 
 /* forward (Phi^T) opcodes */
 /* bit 31 of a word (op >= 8) marks a LEAF: the interpreters test it first (~75% of all words) */
@@ -69,7 +70,9 @@ struct Program {
   std::vector<int32_t> slot_term;           /* slot -> term index, -1 for padding */
   /* brute-force form (fallback kernels, getmat): CSR of packed columns per term */
   std::vector<uint32_t> csr_ptr, csr_col;
+  std::vector<u64> col_use;                 /* loads of each packed column per stream pass (cols are sorted by it) */
   u64 W = 0, nodes = 0, maxdepth = 0, Lcols = 0;
+  int tmem_cap = 0;                         /* >0: words address columns >= cap as 0x8000|(col-cap) (shared memory side) */
   int fwd_stack = 1, bwd_stack = 1;         /* register-stack slots the streams touch (1 + highest index) */
   bool fast_ok = true;                      /* false: deeper than kMaxDepth or duplicate terms */
   u64 nslots() const { return slot_base.empty() ? 0 : slot_base.back(); }
@@ -83,10 +86,15 @@ struct Node {
 } // namespace detail
 
 /* terms: K x d column-major; G: warps per CTA; aug_dim: -1 or the dimension to augment */
-inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) {
+inline uint32_t word_col(const Program& P, uint32_t w) {
+  const uint32_t c = w & 0xFFFFu;
+  return (P.tmem_cap > 0 && (c & 0x8000u)) ? (uint32_t)P.tmem_cap + (c & 0x7FFFu) : c;
+}
+
+inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1, int tmem_cap = 0) {
   using detail::Node;
   Program P;
-  P.K = K; P.d = d; P.G = G; P.aug_dim = aug_dim;
+  P.K = K; P.d = d; P.G = G; P.aug_dim = aug_dim; P.tmem_cap = tmem_cap;
   /* ---- packed column table */
   std::vector<u64> lmax(d, 0);
   for (u64 l = 0; l < d; ++l) for (u64 k = 0; k < K; ++k) lmax[l] = std::max(lmax[l], terms[k + l * K]);
@@ -102,7 +110,7 @@ inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) 
     for (u64 j = 1; j <= lmax[l]; ++j) P.cols.push_back({(uint32_t)l, (uint32_t)j, 0u});
   }
   for (u64 l = 0; l < d; ++l) P.Lcols += lmax[l];
-  if (P.cols.size() > 0xFFFF) P.fast_ok = false;
+  if (P.cols.size() > 0x7FFF) P.fast_ok = false;
   /* ---- per-term paths, CSR, W */
   P.csr_ptr.assign(K + 1, 0);
   std::vector<std::vector<int>> paths(K);
@@ -262,6 +270,7 @@ inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) 
     const uint32_t nreal = (uint32_t)slots.size();
     while (slots.size() % kEmitBatch) { fw.push_back(mkword(F_EMITZERO, 0, FLAG_EMIT, 0)); slots.push_back(-1); }
     for (int i = 0; i <= kPrefetch; ++i) fw.push_back(mkword(F_END, 0, 0, 0));
+    while (fw.size() % 4) fw.push_back(mkword(F_END, 0, 0, 0)); /* streams start 16-byte aligned: 4-word fetches */
     /* backward: exact reverse node order of the forward stream */
     struct Bwd {
       const std::vector<Node>& nd; std::vector<uint32_t>& bw;
@@ -305,6 +314,7 @@ inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) 
       }
     }
     for (int i = 0; i <= kPrefetch; ++i) bw.push_back(mkword(B_END, 0, 0, 0));
+    while (bw.size() % 4) bw.push_back(mkword(B_END, 0, 0, 0));
     P.fwd_off[g + 1] = P.fwd_off[g] + (uint32_t)fw.size();
     P.bwd_off[g + 1] = P.bwd_off[g] + (uint32_t)bw.size();
     P.fwd.insert(P.fwd.end(), fw.begin(), fw.end());
@@ -312,6 +322,34 @@ inline Program compile(const u64* terms, u64 K, u64 d, int G, int aug_dim = -1) 
     P.slot_real[g] = nreal;
     P.slot_base[g + 1] = P.slot_base[g] + (uint32_t)slots.size();
     P.slot_term.insert(P.slot_term.end(), slots.begin(), slots.end());
+  }
+  { /* order the packed columns by how often the streams load them (hottest first): the v2 kernels
+       keep columns [0, lt) in TMEM and the rest in shared memory */
+    const size_t nc = P.cols.size();
+    std::vector<u64> use(nc, 0);
+    for (uint32_t w : P.fwd) { const uint32_t op = w >> 28; if (op >= 8 || op == F_DESC_CUR || op == F_DESC_STK) use[w & 0xFFFFu]++; }
+    std::vector<uint32_t> order(nc), rank(nc);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return use[a] > use[b]; });
+    for (uint32_t i = 0; i < nc; ++i) rank[order[i]] = i;
+    std::vector<ColRef> nc_cols(nc);
+    for (uint32_t i = 0; i < nc; ++i) nc_cols[i] = P.cols[order[i]];
+    P.cols = nc_cols;
+    P.col_use.resize(nc);
+    for (uint32_t i = 0; i < nc; ++i) P.col_use[i] = use[order[i]];
+    auto remap = [&](std::vector<uint32_t>& ws, bool fwd) {
+      for (uint32_t& w : ws) {
+        const uint32_t op = w >> 28;
+        const bool hascol = fwd ? (op >= 8 || op == F_DESC_CUR || op == F_DESC_STK) : (op >= 8 || op == B_CLOSE_FRESH || op == B_CLOSE_LOAD);
+        if (hascol) {
+          uint32_t c = rank[w & 0xFFFFu];
+          if (tmem_cap > 0 && c >= (uint32_t)tmem_cap) c = 0x8000u | (c - (uint32_t)tmem_cap);
+          w = (w & 0xFFFF0000u) | c;
+        }
+      }
+    };
+    remap(P.fwd, true); remap(P.bwd, false);
+    for (uint32_t& c : P.csr_col) c = rank[c];
   }
   for (uint32_t w : P.fwd) {
     const uint32_t op = w >> 28, e = (w >> 24) & 15, fl = (w >> 20) & 15;
@@ -336,7 +374,7 @@ inline double run_bwd_row(const Program& P, const double* Bcols, const double* a
     double cur = 0, stk[kMaxDepth + 1] = {0};
     int slot = (int)P.slot_base[g] + (int)P.slot_real[g] - 1;
     for (uint32_t i = P.bwd_off[g];; ++i) {
-      const uint32_t w = P.bwd[i], op = w >> 28, e = (w >> 24) & 15, fl = (w >> 20) & 15, col = w & 0xFFFF;
+      const uint32_t w = P.bwd[i], op = w >> 28, e = (w >> 24) & 15, fl = (w >> 20) & 15, col = word_col(P, w);
       if (op == B_END) break;
       if (op == B_LEAF) cur += Bcols[col] * a[P.slot_term[slot--]];
       else if (op == B_CLOSE_FRESH || op == B_CLOSE_LOAD) {
@@ -355,7 +393,7 @@ inline void run_fwd_row(const Program& P, const double* Bcols, double b, double*
     stk[0] = b;
     int slot = (int)P.slot_base[g];
     for (uint32_t i = P.fwd_off[g];; ++i) {
-      const uint32_t w = P.fwd[i], op = w >> 28, e = (w >> 24) & 15, fl = (w >> 20) & 15, col = w & 0xFFFF;
+      const uint32_t w = P.fwd[i], op = w >> 28, e = (w >> 24) & 15, fl = (w >> 20) & 15, col = word_col(P, w);
       if (op == F_END) break;
       double emit = 0;
       if (op == F_LEAF) emit = cur * Bcols[col];
