@@ -155,6 +155,34 @@ int ob_outerbase_tmm_mat_dev(ob_outerbase* ob, int sq, const double* A_dev, uint
 int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uint64_t* nodes,
                              uint64_t* maxdepth);
 
+/* ---- terms-specialised kernels (outerbase_b200/csrc/ob_spec.hpp, ob_spec_scaffold.inc).
+ * A terms table stays fixed for every product of a fit (each CG iteration of each optcg,
+ * src/fit.cpp:71-85), so the library can compile Phi a / Phi^T r kernels FOR that table at run
+ * time (NVRTC, sm_100a): the table becomes straight-line FP64 code with its hot basis columns in
+ * registers instead of being interpreted from shared memory.  The reference has no counterpart:
+ * it is the GPU analogue of its `vertpl` / `chunksize` loop tuning (src/modandbase.cpp:504-513).
+ * Policy, per context ("spec" option; environment OB_SPEC=0|1|auto sets the initial value):
+ *   0  never        -- interpreter kernels only
+ *   1  at first use -- compile when a table is first multiplied
+ *   2  auto         -- (default) once a table has proven hot ("spec_work" row-terms, default
+ *                      4e12) or when its module is already in the disk cache
+ *                      ($OB_SPEC_CACHE, default ~/.cache/outerbase_b200, "0" disables)
+ * ob_outerbase_specialize compiles NOW for one table (like planning an FFT) and reports the
+ * seconds spent compiling (0 on a cache hit).  Results of the two kernel families agree to
+ * rounding (<= 1e-12 relative), not bitwise: the summation trees differ. */
+int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
+int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
+/* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */
+int ob_outerbase_spec_state(ob_outerbase* ob, const uint64_t* terms, uint64_t K, int* state);
+/* Test hook (no GPU needed): the CUDA source the generator emits for a table.  opts9 = {wa, ra,
+ * pa, cache_a, wt, rt, pt, cache_t, acc_cap} or NULL for the defaults.  Call with buf = NULL to
+ * get the length; info = {types, accumulators per thread, tile rows Phi a, tile rows Phi^T}. */
+int ob_spec_source(const uint64_t* terms, uint64_t K, uint64_t d, const int* opts9, char* buf,
+                   uint64_t* len, uint64_t* info /* 4 */);
+/* Test hook (no GPU needed): compile a source for sm_100a with NVRTC, bypassing the disk
+ * cache; returns the cubin size. */
+int ob_spec_compile_check(const char* source, uint64_t* cubin_bytes, double* seconds);
+
 /* Host-side self check of the terms compiler (outerbase_b200/csrc/ob_terms.hpp): evaluates
  * ONE row on the CPU by interpreting the compiled warp programs -- bcols holds that row's
  * basemat (M values, knotptst layout).  out_phi_a = sum_k a_k prod_l B[t_kl] ;

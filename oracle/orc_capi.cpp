@@ -71,6 +71,12 @@ int orc_ctx_comm_init(orc_ctx*, int, int, const void*) { g_err = "oracle is sing
 int orc_ctx_comm_info(orc_ctx*, int* n, int* r) { *n = 1; *r = 0; return ORC_OK; }
 int orc_ctx_fp64_peak(orc_ctx*, double* t) { *t = 0; return ORC_OK; }
 int orc_ctx_launch_count(orc_ctx*, uint64_t* c) { *c = 0; return ORC_OK; }
+/* kernel specialisation is a property of the CUDA product; the oracle accepts and ignores the requests */
+int orc_ctx_set_option(orc_ctx*, const char*, double) { return ORC_OK; }
+int orc_outerbase_specialize(orc_outerbase*, const uint64_t*, uint64_t, double* s) { if (s) *s = 0; return ORC_OK; }
+int orc_outerbase_spec_state(orc_outerbase*, const uint64_t*, uint64_t, int* st) { if (st) *st = 0; return ORC_OK; }
+int orc_spec_source(const uint64_t*, uint64_t, uint64_t, const int*, char*, uint64_t*, uint64_t*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
+int orc_spec_compile_check(const char*, uint64_t*, double*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
 
 int orc_covf_numhyp(const char* name, uint64_t* n) { ORC_TRY *n = make_covf(name)->numhyp; ORC_CATCH }
 int orc_covf_cov(orc_ctx*, const char* name, const double* hyp, const double* x1, uint64_t n1,

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def _sources():
-    return [CSRC / "ob_kernels.cu", CSRC / "ob_capi.cu"]
+    return [CSRC / "ob_kernels.cu", CSRC / "ob_spec_rt.cu", CSRC / "ob_capi.cu"]
 
 
 def _stale() -> bool:

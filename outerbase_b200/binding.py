@@ -85,6 +85,27 @@ class Library:
         self.call("ctx_stream", self.ctx, C.byref(s))
         return s.value or 0
 
+    def set_option(self, name: str, value: float):
+        """Context options; "spec" = 0 never | 1 at first use | 2 auto (terms-specialised kernels)."""
+        self.call("ctx_set_option", self.ctx, name.encode(), C.c_double(value))
+
+    def spec_source(self, terms, opts=None):
+        """CUDA source the generator emits for a terms table (host only) -> (source, info)."""
+        t = _terms(terms)
+        o = (C.c_int * 9)(*opts) if opts is not None else None
+        n = C.c_uint64(0)
+        info = (C.c_uint64 * 4)()
+        self.call("spec_source", _p(t), _u(t.shape[0]), _u(t.shape[1]), o, None, C.byref(n), info)
+        buf = C.create_string_buffer(n.value)
+        self.call("spec_source", _p(t), _u(t.shape[0]), _u(t.shape[1]), o, buf, C.byref(n), info)
+        return buf.value.decode(), dict(types=info[0], nacc=info[1], tile_rows_a=info[2], tile_rows_t=info[3])
+
+    def spec_compile_check(self, source: str):
+        """NVRTC-compile a generated source for sm_100a (no GPU needed) -> (cubin bytes, seconds)."""
+        nb, sec = C.c_uint64(0), C.c_double(0)
+        self.call("spec_compile_check", source.encode(), C.byref(nb), C.byref(sec))
+        return nb.value, sec.value
+
     def fp64_peak(self) -> float:
         v = C.c_double()
         self.call("ctx_fp64_peak", self.ctx, C.byref(v))
@@ -347,6 +368,19 @@ class outerbase(_Handle):
 
     def build(self):
         self._lib.call("outerbase_build", self._h)
+
+    def specialize(self, terms) -> float:
+        """Compile the terms-specialised kernels for this table now; returns the compile seconds."""
+        t = _terms(terms)
+        sec = C.c_double(0)
+        self._lib.call("outerbase_specialize", self._h, _p(t), _u(t.shape[0]), C.byref(sec))
+        return sec.value
+
+    def spec_state(self, terms) -> int:
+        t = _terms(terms)
+        st = C.c_int(0)
+        self._lib.call("outerbase_spec_state", self._h, _p(t), _u(t.shape[0]), C.byref(st))
+        return st.value
 
     def _loopvals(self):
         nt, cs, ls, vp = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()

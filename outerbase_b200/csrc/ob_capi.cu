@@ -233,6 +233,59 @@ int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uin
   OB_CATCH
 }
 
+int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value) {
+  OB_TRY
+  need(ctx, "ctx"); need(name, "name");
+  const std::string n(name);
+  if (n == "spec") {
+    if (value != 0 && value != 1 && value != 2) throw std::invalid_argument("spec must be 0, 1 or 2");
+    ctx->c.spec_mode = (int)value;
+  } else if (n == "spec_work") ctx->c.spec_work = value;
+  else throw std::invalid_argument("unknown option " + n);
+  OB_CATCH
+}
+int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds) {
+  OB_TRY
+  need(ob, "ob"); need(terms, "terms");
+  obe::OuterBase::SpecEntry* e = ob->ob->spec_for(terms, K, /*force=*/true);
+  if (!e) throw std::logic_error("specialisation did not produce a module");
+  if (compile_seconds) *compile_seconds = obd::spec_compile_seconds(*e->k);
+  OB_CATCH
+}
+int ob_outerbase_spec_state(ob_outerbase* ob, const uint64_t* terms, uint64_t K, int* state) {
+  OB_TRY
+  need(ob, "ob"); need(terms, "terms"); need(state, "state");
+  *state = 0;
+  for (const auto& e : ob->ob->specs)
+    if (e.K == K && std::memcmp(e.terms.data(), terms, K * ob->ob->d * sizeof(u64)) == 0) *state = e.state;
+  OB_CATCH
+}
+int ob_spec_source(const uint64_t* terms, uint64_t K, uint64_t d, const int* opts9, char* buf, uint64_t* len, uint64_t* info) {
+  OB_TRY
+  need(terms, "terms"); need(len, "len");
+  obs::SpecOptions o = obd::spec_default_options();
+  if (opts9) { o.wa = opts9[0]; o.ra = opts9[1]; o.pa = opts9[2]; o.cache_a = opts9[3]; o.wt = opts9[4]; o.rt = opts9[5]; o.pt = opts9[6]; o.cache_t = opts9[7]; o.acc_cap = opts9[8]; }
+  const int types = obs::choose_types(terms, K, d, o);
+  if (!types) throw std::invalid_argument("terms table is not trie-compilable");
+  const obt::Program pa = obt::compile(terms, K, d, o.wa), pt = obt::compile(terms, K, d, types * o.wt);
+  const obs::SpecSource S = obs::generate(&pa, &pt, types, o);
+  if (!S.ok) throw std::invalid_argument(S.why);
+  if (info) { info[0] = (u64)S.types; info[1] = (u64)S.nacc; info[2] = (u64)S.tr_a; info[3] = (u64)S.tr_t; }
+  if (buf) {
+    if (*len < S.src.size() + 1) throw std::range_error("buffer too small");
+    std::memcpy(buf, S.src.c_str(), S.src.size() + 1);
+  }
+  *len = S.src.size() + 1;
+  OB_CATCH
+}
+int ob_spec_compile_check(const char* source, uint64_t* cubin_bytes, double* seconds) {
+  OB_TRY
+  need(source, "source");
+  const std::string cubin = obd::spec_compile_nocache(source, seconds);
+  if (cubin_bytes) *cubin_bytes = cubin.size();
+  OB_CATCH
+}
+
 int ob_debug_terms_eval(const uint64_t* terms, uint64_t K, uint64_t d, const uint64_t* knotptst, int ngroups, int aug_dim,
                         const double* bcols, const double* gcols0, const double* a, double b, double* out_phi_a,
                         double* out_phit, uint64_t* stats) {

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "ob_model.hpp"
+#include "ob_spec.hpp"
 #include "ob_terms.hpp"
 
 namespace obd {
@@ -54,6 +55,10 @@ struct Ctx {
   void* comm = nullptr;
   int nranks = 1, rank = 0;
   double* pinned = nullptr; /* small pinned scratch for scalar read-back */
+  /* terms-specialised kernels (ob_spec.hpp): 0 never, 1 at first use, 2 once a table has proven hot
+   * (spec_work row-terms processed by the interpreter kernels) or its module is in the disk cache */
+  int spec_mode = 2;
+  double spec_work = 4e12;
   explicit Ctx(int dev);
   ~Ctx();
   void sync() { OB_CUDA(cudaStreamSynchronize(stream)); }
@@ -142,6 +147,19 @@ int tmem_rows_per_lane(const Ctx& c, u64 N); /* R of the TMEM kernels for N rows
 void launch_phi_a(Ctx& c, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
 /* Phi^T w -> out (K, device); result is the LOCAL (this rank's rows) sum */
 void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
+void launch_phi_t_reduce(Ctx& c, const double* partial, int nblocks, int nslots, const int32_t* slot_term, double* out);
+/* ---- terms-specialised kernels (ob_spec.hpp generator, ob_spec_scaffold.inc frame, ob_spec_rt.cu run time) */
+struct SpecKernels;
+bool spec_compiler_available();
+obs::SpecOptions spec_default_options();
+/* pa: program with G = opt.wa, pt: G = types * opt.wt.  only_if_cached: return null instead of compiling */
+std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const obt::Program& pt, int types, const obs::SpecOptions& opt,
+                                        bool only_if_cached);
+double spec_compile_seconds(const SpecKernels& k);
+std::string spec_compile_nocache(const std::string& src, double* seconds);
+bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol);
+void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
+void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
 /* explicit Phi (N x K column-major, device), getm_ linalg.cpp:685-715 */
 void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo);
 /* sum of n per-CTA partials, fixed order -> out[0] */

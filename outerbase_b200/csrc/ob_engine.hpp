@@ -54,6 +54,19 @@ struct OuterBase {
   std::list<ProgEntry> programs;
   struct ColEntry { const obd::DevProgram* prog; int sq; int h; std::unique_ptr<obd::ColTable> ct; };
   std::list<ColEntry> coltables;
+  /* terms-specialised kernels of one table (ob_spec.hpp): its two programs (Phi a: G = wa streams,
+   * Phi^T: types * wt streams) and the compiled module */
+  struct SpecEntry {
+    std::vector<u64> terms; u64 K = 0;
+    std::unique_ptr<obd::DevProgram> pa, pt;
+    std::shared_ptr<obd::SpecKernels> k;
+    int types = 0;
+    int state = 0;      /* 0 interpreter so far, 1 module ready, -1 not specialisable */
+    bool probed = false; /* disk cache looked up */
+    double work = 0;    /* row-terms sent through the interpreter kernels */
+    std::string why;
+  };
+  std::list<SpecEntry> specs;
   /* terms installed by set_terms for the *_dev entry points */
   std::vector<u64> cur_terms;
   u64 cur_K = 0;
@@ -164,6 +177,74 @@ struct OuterBase {
     return programs.front().prog.get();
   }
 
+  /* ---- specialisation policy (Ctx::spec_mode): returns the ready entry or null (use the interpreter).
+   * `force` compiles now whatever the mode (ob_outerbase_specialize). */
+  SpecEntry* spec_for(const u64* terms, u64 K, bool force = false) {
+    if ((ctx.spec_mode == 0 && !force) || K == 0 || N == 0) return nullptr;
+    if (!om && ctx.spec_mode != 1 && !force) return nullptr; /* one-shot wrappers of the stateless seam */
+    SpecEntry* e = nullptr;
+    for (auto it = specs.begin(); it != specs.end(); ++it)
+      if (it->K == K && std::memcmp(it->terms.data(), terms, K * d * sizeof(u64)) == 0) {
+        specs.splice(specs.begin(), specs, it);
+        e = &specs.front();
+        break;
+      }
+    if (!e) {
+      check_terms(terms, K);
+      specs.emplace_front();
+      e = &specs.front();
+      e->terms.assign(terms, terms + K * d);
+      e->K = K;
+      while (specs.size() > 8) {
+        const SpecEntry& dead = specs.back();
+        coltables.remove_if([&](const ColEntry& c) { return c.prog == dead.pa.get() || c.prog == dead.pt.get(); });
+        specs.pop_back();
+      }
+    }
+    if (e->state == 1) return e;
+    if (e->state < 0) { if (force) throw std::runtime_error("terms table cannot be specialised: " + e->why); return nullptr; }
+    const bool now = force || ctx.spec_mode == 1;
+    e->work += (double)N * (double)K;
+    const bool hot = e->work >= ctx.spec_work;
+    const bool probe = !e->probed && (double)N * (double)K >= 1e8; /* large tables: a cached module is free */
+    if (!now && !hot && !probe) return nullptr;
+    try {
+      const obs::SpecOptions opt = obd::spec_default_options();
+      if (!e->pa) {
+        e->types = obs::choose_types(terms, K, d, opt);
+        if (e->types == 0) throw std::runtime_error("not a trie-compilable table (duplicate or too deep terms)");
+        e->pa.reset(new obd::DevProgram());
+        e->pa->host = obt::compile(terms, K, d, opt.wa);
+        e->pt.reset(new obd::DevProgram());
+        e->pt->host = obt::compile(terms, K, d, e->types * opt.wt);
+        e->pa->upload(ctx.stream);
+        e->pt->upload(ctx.stream);
+        ctx.sync();
+      }
+      e->probed = true;
+      e->k = obd::spec_build(ctx, e->pa->host, e->pt->host, e->types, opt, /*only_if_cached=*/!(now || hot));
+      if (!e->k) return nullptr; /* not in the cache: stay on the interpreter until hot */
+      if (!obd::spec_fits(ctx, *e->k, (int)e->pa->host.cols.size())) throw std::runtime_error("row tile does not fit in shared memory");
+      e->state = 1;
+      return e;
+    } catch (const std::exception& ex) {
+      e->state = -1;
+      e->why = ex.what();
+      e->k.reset();
+      if (now) throw; /* asked for explicitly: fail loudly */
+      return nullptr;
+    }
+  }
+  /* Phi a / Phi^T of the plain table (no hyper-gradient augmentation): specialised kernels when ready */
+  void phi_a(const u64* terms, u64 K, int sq, const obd::PhiAArgs& a, int* grid_out) {
+    if (SpecEntry* e = spec_for(terms, K)) { obd::launch_phi_a_spec(ctx, *e->k, plan(e->pa.get(), sq, -1), a, ws, grid_out); return; }
+    obd::launch_phi_a(ctx, plan(program(terms, K, -1), sq, -1), a, ws, grid_out);
+  }
+  void phi_t(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev) {
+    if (SpecEntry* e = spec_for(terms, K)) { obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), w_dev, out_dev, ws); return; }
+    obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
+  }
+
   obd::ColTable* coltable(const obd::DevProgram* prog, int sq, int h) {
     for (auto& c : coltables) if (c.prog == prog && c.sq == sq && c.h == h) return c.ct.get();
     const obt::Program& P = prog->host;
@@ -206,10 +287,10 @@ struct OuterBase {
   /* ---- device-pointer operations (stream ordered, not synchronised) */
   void mm_dev(const u64* terms, u64 K, int sq, const double* a_dev, double* out_dev) {
     obd::PhiAArgs a; a.a = a_dev; a.out = out_dev; a.mode = obd::PHI_PLAIN;
-    obd::launch_phi_a(ctx, plan(program(terms, K, -1), sq, -1), a, ws, nullptr);
+    phi_a(terms, K, sq, a, nullptr);
   }
   void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true) {
-    obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
+    phi_t(terms, K, sq, w_dev, out_dev);
     if (reduce_ranks) ctx.allreduce_sum(out_dev, K);
   }
   /* prodmmge_: outge column h = augmented-program product (ob_terms.hpp) */
@@ -223,7 +304,7 @@ struct OuterBase {
   }
   void tmm_ge_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev /* K*(1+H): out | outge */) {
     if (!dograd) throw std::logic_error("outerbase was built without gradients");
-    obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
+    phi_t(terms, K, sq, w_dev, out_dev);
     for (u64 h = 0; h < H; ++h)
       obd::launch_phi_t(ctx, plan(program(terms, K, (int)hypmatch[h], 1), sq, (int)h), w_dev, out_dev + (1 + h) * K, ws);
     ctx.allreduce_sum(out_dev, K * (1 + H));
@@ -520,18 +601,17 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     const u64 K = nterms, H = ob.H;
     if (c.size() != K) throw std::range_error("coeff must have one entry per term");
     kbuf.upload(coeff, ctx.stream);
-    obd::DevProgram* pr = ob.program(terms.data(), K, -1);
     obd::PhiAArgs a;
     a.a = kbuf.p; a.out = yhat.p; a.w = w.p; a.y = y.p; a.sd = obssd; a.mode = obd::PHI_UPDATE;
     int grid = 0;
-    obd::launch_phi_a(ctx, ob.plan(pr, 0, -1), a, ob.ws, &grid);
+    ob.phi_a(terms.data(), K, 0, a, &grid);
     yhat_valid = false;
     /* reduction buffer: [grad (K) | ssq | gradhyp (H)] -> one allreduce */
     red.ensure(K + 1 + H);
     OB_CUDA(cudaMemsetAsync(red.p, 0, (K + 1 + H) * sizeof(double), ctx.stream));
     if (grid > 0) obd::launch_sum_partials(ctx, ob.ws.ssq.p, grid, red.p + K);
     const bool dohyp = compute_grad && compute_gradhyp;
-    if (compute_grad) obd::launch_phi_t(ctx, ob.plan(ob.program(terms.data(), K, -1, 1), 0, -1), w.p, red.p, ob.ws);
+    if (compute_grad) ob.phi_t(terms.data(), K, 0, w.p, red.p);
     if (dohyp) { /* gradhyp = residtemp^T * yhatge, :127 -- yhatge column h is never stored */
       gebuf.ensure(ob.ld + 4 * ctx.sms);
       for (u64 h = 0; h < H; ++h) {
@@ -556,12 +636,11 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
   std::vector<double> hessmult(const std::vector<double>& g) override { /* :137-145 */
     const u64 K = nterms;
     kbuf.upload(g, ctx.stream);
-    obd::DevProgram* pr = ob.program(terms.data(), K, -1);
     obd::PhiAArgs a;
     a.a = kbuf.p; a.w = w.p; a.sd = obssd; a.mode = obd::PHI_HESS;
-    obd::launch_phi_a(ctx, ob.plan(pr, 0, -1), a, ob.ws, nullptr);
+    ob.phi_a(terms.data(), K, 0, a, nullptr);
     red.ensure(K);
-    obd::launch_phi_t(ctx, ob.plan(ob.program(terms.data(), K, -1, 1), 0, -1), w.p, red.p, ob.ws);
+    ob.phi_t(terms.data(), K, 0, w.p, red.p);
     ctx.allreduce_sum(red.p, K);
     std::vector<double> o(K);
     ob.d2h(o.data(), red.p, K);

@@ -783,6 +783,10 @@ Ctx::Ctx(int dev) : device(dev) {
   smem_optin = prop.sharedMemPerBlockOptin;
   OB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   OB_CUDA(cudaMallocHost(&pinned, 4096 * sizeof(double)));
+  if (const char* e = getenv("OB_SPEC")) { /* 0 | 1 | auto */
+    const std::string v(e);
+    spec_mode = v == "0" ? 0 : (v == "1" ? 1 : 2);
+  }
 }
 
 Ctx::~Ctx() {
@@ -1033,6 +1037,11 @@ void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Works
 #undef OB_LAUNCH_T
   check_launch(c, "phi_t_kernel");
   phi_t_reduce_kernel<<<(p.nslots + 127) / 128, 128, 0, c.stream>>>(p.partial, grid, p.nslots, pr.slot_term.p, out);
+  check_launch(c, "phi_t_reduce_kernel");
+}
+
+void launch_phi_t_reduce(Ctx& c, const double* partial, int nblocks, int nslots, const int32_t* slot_term, double* out) {
+  phi_t_reduce_kernel<<<(nslots + 127) / 128, 128, 0, c.stream>>>(partial, nblocks, nslots, slot_term, out);
   check_launch(c, "phi_t_reduce_kernel");
 }
 

@@ -1,0 +1,352 @@
+/*
+ * ob_spec.hpp -- generator of the terms-specialised Phi kernels (host side, plain C++).
+ *
+ * Partial evaluation of the two stream interpreters of ob_terms.hpp (run_bwd_row /
+ * run_fwd_row, the CPU statements of what phi_a_kernel / phi_t_kernel do) on ONE compiled
+ * terms table: every word of a warp's stream becomes one or two FP64 statements of
+ * straight-line CUDA C, the register stack becomes named variables, and the factor
+ * columns a stream reads more than once are loaded into registers once per 32R rows.
+ * The result is spliced into the hand-written frame ob_spec_scaffold.inc and compiled
+ * for sm_100a with NVRTC by ob_kernels.cu.  Semantics and operation order are those of
+ * the interpreters, i.e. of prodmm_/tprodmm_ (src/linalg.cpp:57-131, 286-355) up to the
+ * trie re-association documented in ob_terms.hpp.
+ */
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ob_terms.hpp"
+
+namespace obs {
+
+using obt::Program;
+using u64 = uint64_t;
+
+/* mirrored by `struct SpecParams` in ob_spec_scaffold.inc */
+struct SpecParams {
+  const double* const* load_src;
+  const int* col_op;
+  const double* scale;
+  const double* y;
+  const double* win;
+  double* out;
+  double* w;
+  double* ssq_partial;
+  double* partial;
+  const double* a;
+  const int* slot_term;
+  double sd;
+  unsigned long long N;
+  int ncol, has_ops, sq, mode, ntiles, nbuf, nslots;
+  unsigned off_tile, tile_doubles, off_part, off_vec;
+};
+
+struct SpecOptions {
+  /* Phi a: streams, rows per lane, passes per tile, register-cached columns per stream, row groups
+   * (compute warps = wa * qa) */
+  int wa = 2, ra = 1, pa = 4, cache_a = 60, qa = 4;
+  /* Phi^T: warps per CTA, rows per lane, passes per tile, cached columns, accumulators per warp (cap) */
+  int wt = 12, rt = 1, pt = 4, cache_t = 20, acc_cap = 44;
+};
+
+struct SpecSource {
+  std::string src;
+  int types = 0, nacc = 0; /* Phi^T: CTA types, accumulators declared per thread */
+  int tr_a = 0, tr_t = 0;  /* rows per tile */
+  SpecOptions opt;
+  bool ok = false;
+  std::string why;
+};
+
+namespace detail {
+
+struct Emitter {
+  std::string s;
+  char buf[512];
+  template <class... A>
+  void f(const char* fmt, A... a) { std::snprintf(buf, sizeof buf, fmt, a...); s += buf; }
+  void f(const char* lit) { s += lit; }
+};
+
+/* factor access for one stream: cached columns become variables, the rest load at every use */
+struct Factors {
+  std::vector<int> cached; /* -1 / 1 per column */
+  std::vector<char> declared;
+  int R, TR;
+  Factors(const Program& P, const std::vector<uint32_t>& words, uint32_t lo, uint32_t hi, bool fwd, int cache, int R_, int TR_)
+      : R(R_), TR(TR_) {
+    const size_t nc = P.cols.size();
+    std::vector<int> use(nc, 0);
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t w = words[i], op = w >> 28;
+      const bool hascol = fwd ? (op >= 8 || op == obt::F_DESC_CUR || op == obt::F_DESC_STK)
+                              : (op >= 8 || op == obt::B_CLOSE_FRESH || op == obt::B_CLOSE_LOAD);
+      if (hascol) use[w & 0xFFFFu]++;
+    }
+    std::vector<int> order(nc);
+    for (size_t i = 0; i < nc; ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return use[a] > use[b]; });
+    cached.assign(nc, 0);
+    declared.assign(nc, 0);
+    for (int i = 0; i < (int)nc && i < cache; ++i) if (use[order[i]] >= 2) cached[order[i]] = 1;
+  }
+  /* expression for factor (col, r); may first emit the declaration of a cached column */
+  std::string get(Emitter& e, int col, int r) {
+    char b[96];
+    const unsigned off = (unsigned)(col * TR + 32 * r) * 8u;
+    if (!cached[col]) { std::snprintf(b, sizeof b, "ldv(tp + %uu)", off); return b; }
+    if (!declared[col]) {
+      declared[col] = 1;
+      for (int q = 0; q < R; ++q) e.f("const double f%d_%d = lds(tp + %uu);\n", col, q, (unsigned)(col * TR + 32 * q) * 8u);
+    }
+    std::snprintf(b, sizeof b, "f%d_%d", col, r);
+    return b;
+  }
+};
+
+/* backward (Horner) stream g -> statements accumulating into o[r] */
+inline void emit_bwd(Emitter& e, const Program& P, int g, int R, int TR, int cache) {
+  using namespace obt;
+  Factors F(P, P.bwd, P.bwd_off[g], P.bwd_off[g + 1], false, cache, R, TR);
+  int slot = (int)P.slot_base[g] + (int)P.slot_real[g] - 1;
+  int nv = 0;
+  /* symbolic values: "" = known zero, else a variable stem (stem_r) */
+  std::string cur, stk[kMaxDepth + 2];
+  auto fresh = [&]() { char b[24]; std::snprintf(b, sizeof b, "x%d", nv++); return std::string(b); };
+  /* coefficient of slot k -> variable a<k>.  Slots are consumed downwards: an odd slot fetches
+   * the aligned pair (k-1, k) with one broadcast LDS.128, the even partner is used next. */
+  const int slot_lo = (int)P.slot_base[g];
+  std::vector<char> have(P.nslots() + 2, 0);
+  auto coef = [&](int k) {
+    if (have[k]) return;
+    if ((k & 1) && k - 1 >= slot_lo) {
+      e.f("double a%d, a%d; lda2<%d>(as, a%d, a%d);\n", k - 1, k, 8 * (k - 1), k - 1, k);
+      have[k - 1] = have[k] = 1;
+    } else {
+      e.f("const double a%d = lda<%d>(as);\n", k, 8 * k);
+      have[k] = 1;
+    }
+  };
+  for (uint32_t i = P.bwd_off[g];; ++i) {
+    const uint32_t w = P.bwd[i], op = w >> 28, d = (w >> 24) & 15, fl = (w >> 20) & 15, col = w & 0xFFFFu;
+    if (op == B_END) break;
+    if (op == B_LEAF) {
+      const int k = slot--;
+      const std::string x = fresh();
+      coef(k);
+      for (int r = 0; r < R; ++r) {
+        const std::string f = F.get(e, (int)col, r);
+        if (cur.empty()) e.f("const double %s_%d = %s * a%d;\n", x.c_str(), r, f.c_str(), k);
+        else e.f("const double %s_%d = fma(%s, a%d, %s_%d);\n", x.c_str(), r, f.c_str(), k, cur.c_str(), r);
+      }
+      cur = x;
+    } else if (op == B_CLOSE_FRESH || op == B_CLOSE_LOAD) {
+      const bool has_a = fl & FLAG_HAS_A;
+      const int k = has_a ? slot-- : -1;
+      const std::string base = (op == B_CLOSE_LOAD) ? stk[d - 1] : std::string();
+      const std::string x = fresh();
+      if (has_a) coef(k);
+      for (int r = 0; r < R; ++r) {
+        const std::string f = F.get(e, (int)col, r);
+        char val[96];
+        if (has_a && !cur.empty()) std::snprintf(val, sizeof val, "(a%d + %s_%d)", k, cur.c_str(), r);
+        else if (has_a) std::snprintf(val, sizeof val, "a%d", k);
+        else if (!cur.empty()) std::snprintf(val, sizeof val, "%s_%d", cur.c_str(), r);
+        else std::snprintf(val, sizeof val, "0.0");
+        if (base.empty()) e.f("const double %s_%d = %s * %s;\n", x.c_str(), r, f.c_str(), val);
+        else e.f("const double %s_%d = fma(%s, %s, %s_%d);\n", x.c_str(), r, f.c_str(), val, base.c_str(), r);
+      }
+      if (op == B_CLOSE_LOAD) stk[d - 1].clear();
+      cur = x;
+    } else if (op == B_SAVE) {
+      stk[d] = cur;
+      cur.clear();
+    } else if (op == B_ROOT) {
+      const int k = slot--;
+      const std::string x = fresh();
+      coef(k);
+      for (int r = 0; r < R; ++r) {
+        if (cur.empty()) e.f("const double %s_%d = a%d;\n", x.c_str(), r, k);
+        else e.f("const double %s_%d = %s_%d + a%d;\n", x.c_str(), r, cur.c_str(), r, k);
+      }
+      cur = x;
+    }
+  }
+  if (!cur.empty()) for (int r = 0; r < R; ++r) e.f("o[%d] = %s_%d;\n", r, cur.c_str(), r);
+}
+
+/* forward (top-down) stream g -> statements accumulating into acc<i>; returns the emit count */
+inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cache) {
+  using namespace obt;
+  Factors F(P, P.fwd, P.fwd_off[g], P.fwd_off[g + 1], true, cache, R, TR);
+  int nv = 0, ia = 0;
+  std::string cur = "b", stk[kMaxDepth + 2];
+  stk[0] = "b";
+  auto name = [&](const std::string& stem, int r) {
+    char b[48];
+    if (stem == "b") std::snprintf(b, sizeof b, "b[%d]", r);
+    else std::snprintf(b, sizeof b, "%s_%d", stem.c_str(), r);
+    return std::string(b);
+  };
+  auto fresh = [&]() { char b[24]; std::snprintf(b, sizeof b, "v%d", nv++); return std::string(b); };
+  for (uint32_t i = P.fwd_off[g];; ++i) {
+    const uint32_t w = P.fwd[i], op = w >> 28, d = (w >> 24) & 15, fl = (w >> 20) & 15, col = w & 0xFFFFu;
+    if (op == F_END) break;
+    if (op == F_LEAF) {
+      for (int r = 0; r < R; ++r) {
+        const std::string f = F.get(e, (int)col, r);
+        e.f("acc%d = fma(%s, %s, acc%d);\n", ia, name(cur, r).c_str(), f.c_str(), ia);
+      }
+      ++ia;
+    } else if (op == F_DESC_CUR || op == F_DESC_STK) {
+      const std::string src = (op == F_DESC_STK) ? stk[d - 1] : cur;
+      const std::string x = fresh();
+      for (int r = 0; r < R; ++r) {
+        const std::string f = F.get(e, (int)col, r);
+        e.f("const double %s_%d = %s * %s;\n", x.c_str(), r, name(src, r).c_str(), f.c_str());
+      }
+      cur = x;
+      if (fl & FLAG_SAVE) stk[d] = x;
+      if (fl & FLAG_EMIT) {
+        for (int r = 0; r < R; ++r) e.f("acc%d += %s_%d;\n", ia, x.c_str(), r);
+        ++ia;
+      }
+    } else if (op == F_ROOT) {
+      for (int r = 0; r < R; ++r) e.f("acc%d += b[%d];\n", ia, r);
+      ++ia;
+    } else if (op == F_LOADCUR) {
+      cur = stk[d];
+    } /* F_EMITZERO: padding of the interpreter's emit batches, nothing to do */
+  }
+  return ia;
+}
+
+inline void replace_marker(std::string& s, const char* marker, const std::string& with) {
+  const size_t at = s.find(marker);
+  if (at == std::string::npos) throw std::logic_error(std::string("scaffold marker missing: ") + marker);
+  s.replace(at, std::strlen(marker), with);
+}
+
+} // namespace detail
+
+inline const char* scaffold_text() {
+  static const char* text =
+#include "ob_spec_scaffold.inc"
+      ;
+  return text;
+}
+
+/* Phi^T: smallest number of CTA types (streams = types * wt) whose busiest stream keeps its
+ * accumulators within the cap.  0: the table is not trie-compilable. */
+inline int choose_types(const u64* terms, u64 K, u64 d, const SpecOptions& opt) {
+  if (K == 0) return 0;
+  int types = (int)std::max<u64>(1, (K + (u64)opt.wt * opt.acc_cap - 1) / ((u64)opt.wt * opt.acc_cap));
+  for (; types <= 64; ++types) {
+    const Program P = obt::compile(terms, K, d, types * opt.wt);
+    if (!P.fast_ok) return 0;
+    u64 mx = 0;
+    for (uint32_t r : P.slot_real) mx = std::max<u64>(mx, r);
+    if ((int)mx <= opt.acc_cap) return types;
+  }
+  return 0;
+}
+
+/* pa: program compiled with G = opt.wa (or null: no Phi a kernel); pt: G = types * opt.wt (or null) */
+inline SpecSource generate(const Program* pa, const Program* pt, int types, const SpecOptions& opt) {
+  using namespace detail;
+  SpecSource S;
+  S.opt = opt;
+  S.tr_a = 32 * opt.ra * opt.pa;
+  S.tr_t = 32 * opt.rt * opt.pt;
+  const bool want_a = pa != nullptr, want_t = pt != nullptr;
+  if (!want_a && !want_t) { S.why = "nothing to generate"; return S; }
+  const u64 K = want_a ? pa->K : pt->K;
+  if (K == 0) { S.why = "no terms"; return S; }
+  if (256 % S.tr_a || 256 % S.tr_t || S.tr_a > 32 * opt.wa * opt.qa || opt.pa % opt.qa || opt.wa * opt.qa > 31) {
+    S.why = "inconsistent tile options";
+    return S;
+  }
+  if ((want_a && (!pa->fast_ok || pa->G != opt.wa || pa->tmem_cap)) || (want_t && (!pt->fast_ok || pt->G != types * opt.wt || pt->tmem_cap))) {
+    S.why = "programs do not match the options";
+    return S;
+  }
+  Emitter hdr, tab, ca, ct, decl, red;
+  hdr.f("#define OBS_PARAM_BYTES %d\n#define OBS_K %llu\n", (int)sizeof(SpecParams), (unsigned long long)K);
+  if (want_a) {
+    const Program& P = *pa;
+    hdr.f("#define OBS_HAVE_A 1\n#define OBS_WA %d\n#define OBS_RA %d\n#define OBS_PA %d\n#define OBS_QA %d\n#define OBS_NCOLS_A %d\n",
+          opt.wa, opt.ra, opt.pa, opt.qa, (int)P.cols.size());
+    tab.f("__device__ const unsigned short obs_cols_a[] = {");
+    for (size_t c = 0; c < P.cols.size(); ++c) tab.f("%d,", (int)c);
+    tab.f("0};\n");
+    for (int g = 0; g < opt.wa; ++g) {
+      ca.f("case %d: {\n", g);
+      emit_bwd(ca, P, g, opt.ra, S.tr_a, opt.cache_a);
+      ca.f("} break;\n");
+    }
+  }
+  if (want_t) {
+    const Program& P = *pt;
+    u64 mx = 0;
+    for (uint32_t r : P.slot_real) mx = std::max<u64>(mx, r);
+    S.nacc = (int)mx;
+    S.types = types;
+    const int G = types * opt.wt;
+    hdr.f("#define OBS_HAVE_T 1\n#define OBS_WT %d\n#define OBS_RT %d\n#define OBS_PT %d\n#define OBS_TYPES %d\n", opt.wt, opt.rt,
+          opt.pt, types);
+    /* per-type column lists */
+    std::vector<std::vector<int>> tcols(types);
+    for (int g = 0; g < G; ++g) {
+      std::vector<char> used(P.cols.size(), 0);
+      for (uint32_t i = P.fwd_off[g]; i < P.fwd_off[g + 1]; ++i) {
+        const uint32_t w = P.fwd[i], op = w >> 28;
+        if (op >= 8 || op == obt::F_DESC_CUR || op == obt::F_DESC_STK) used[w & 0xFFFFu] = 1;
+      }
+      auto& tc = tcols[g / opt.wt];
+      for (size_t c = 0; c < used.size(); ++c) if (used[c] && std::find(tc.begin(), tc.end(), (int)c) == tc.end()) tc.push_back((int)c);
+    }
+    size_t maxcols = 1;
+    for (auto& tc : tcols) maxcols = std::max(maxcols, tc.size());
+    hdr.f("#define OBS_NQ_T %d\n", (int)std::max<size_t>(1, (maxcols + 31) / 32));
+    tab.f("__device__ const unsigned short obs_cols_t[] = {");
+    std::vector<int> coff{0};
+    for (auto& tc : tcols) { std::sort(tc.begin(), tc.end()); for (int c : tc) tab.f("%d,", c); coff.push_back(coff.back() + (int)tc.size()); }
+    tab.f("0};\n__device__ const unsigned short obs_coff_t[] = {");
+    for (int v : coff) tab.f("%d,", v);
+    tab.f("};\n__device__ const unsigned obs_slot_base[] = {");
+    for (int g = 0; g < G; ++g) tab.f("%u,", P.slot_base[g]);
+    tab.f("};\n__device__ const unsigned short obs_slot_real[] = {");
+    for (int g = 0; g < G; ++g) tab.f("%u,", P.slot_real[g]);
+    tab.f("};\n");
+    for (int g = 0; g < G; ++g) {
+      ct.f("case %d: {\n", g);
+      const int n = emit_fwd(ct, P, g, opt.rt, S.tr_t, opt.cache_t);
+      if (n != (int)P.slot_real[g]) { S.why = "emit count mismatch"; return S; }
+      ct.f("} break;\n");
+    }
+    for (int i = 0; i < S.nacc; ++i) decl.f("  double acc%d = 0.0;\n", i);
+    /* one butterfly per accumulator, once per launch; lane 0 stores */
+    for (int i = 0; i < S.nacc; ++i) {
+      red.f("    { double v = acc%d;", i);
+      for (int m = 16; m > 0; m >>= 1) red.f(" v += shfl_xor_d(v, %d);", m);
+      red.f(" if (lane == 0 && %d < nacc) dst[%d] = v; }\n", i, i);
+    }
+  }
+  std::string body = scaffold_text();
+  replace_marker(body, "//@@TABLES@@", tab.s);
+  if (want_a) replace_marker(body, "//@@CASES_A@@", ca.s);
+  if (want_t) {
+    replace_marker(body, "//@@ACC_DECL@@", decl.s);
+    replace_marker(body, "//@@CASES_T@@", ct.s);
+    replace_marker(body, "//@@ACC_REDUCE@@", red.s);
+  }
+  S.src = hdr.s + body;
+  S.ok = true;
+  return S;
+}
+
+} // namespace obs

@@ -1,0 +1,139 @@
+"""GPU parity tests of the TERMS-SPECIALISED kernels (ob_spec.hpp / ob_spec_scaffold.inc):
+the same C-ABI calls as tests/test_gpu_parity.py with the context option spec = 1, so every
+plain Phi a / Phi^T r product runs on the run-time compiled kernels.  Same tolerances: matvecs
+1e-12 relative on bit-identical basemat (north_star), fits 1e-8.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_problem, relerr
+from test_gpu_parity import MATVEC_TOL, _lpdf_pair, oracle_basis
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def spec(gpu):
+    gpu.set_option("spec", 1)
+    yield gpu
+    gpu.set_option("spec", 2)
+
+
+@pytest.mark.parametrize("N,K", [(15, 20), (200, 100), (10000, 100), (200, 1000), (10000, 2000)])
+def test_spec_seam_matvecs_on_oracle_basis(spec, oracle, N, K):
+    o = oracle_basis(oracle, N, K)
+    terms, rng = o["terms"], o["rng"]
+    a = np.sqrt(o["om"].getvar(terms) / 20) * rng.normal(size=K)
+    r = rng.normal(size=N)
+    n0 = spec.launch_count()
+    assert relerr(spec.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
+    assert relerr(spec.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+    assert spec.launch_count() >= n0 + 3  # phi_a_spec, phi_t_spec, reduce
+
+
+@pytest.mark.parametrize("N", [1, 31, 127, 128, 129, 255, 256, 257, 1000])
+def test_spec_ragged_row_counts(spec, oracle, N):
+    o = oracle_basis(oracle, N, 40)
+    terms, rng = o["terms"], o["rng"]
+    a, r = rng.normal(size=40), rng.normal(size=N)
+    assert relerr(spec.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
+    assert relerr(spec.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+
+
+def test_spec_degenerate_terms(spec, oracle):
+    o = oracle_basis(oracle, 100, 30)
+    rng = o["rng"]
+    for terms in (o["terms"][:1], o["terms"][1:2], o["terms"][::-1][:7], np.asfortranarray(o["terms"][[3, 9, 17]])):
+        terms = np.asfortranarray(terms)
+        a, r = rng.normal(size=terms.shape[0]), rng.normal(size=100)
+        assert relerr(spec.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
+        assert relerr(spec.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
+
+
+def test_spec_agrees_with_interpreter_and_state(gpu, oracle):
+    """Same object, same inputs: interpreter kernels first, then the specialised ones."""
+    om, x, y, terms, rng = make_problem(gpu, 5000, 300)
+    ob = gpu.outerbase(om, x)
+    a, r = rng.normal(size=300), rng.normal(size=5000)
+    gpu.set_option("spec", 0)
+    try:
+        y0, t0, s0 = ob.matmul(terms, a), ob.tmatmul(terms, r), ob.sqtmm(terms, r)
+        assert ob.spec_state(terms) == 0
+        ob.specialize(terms)  # explicit request works whatever the policy
+        assert ob.spec_state(terms) == 1
+        gpu.set_option("spec", 2)
+        y1, t1, s1 = ob.matmul(terms, a), ob.tmatmul(terms, r), ob.sqtmm(terms, r)
+    finally:
+        gpu.set_option("spec", 2)
+    assert relerr(y1, y0) < 1e-13 and relerr(t1, t0) < 1e-13 and relerr(s1, s0) < 1e-13
+    np.testing.assert_array_equal(t1, ob.tmatmul(terms, r))  # run-to-run bit reproducible
+
+
+def test_spec_squared_operators(spec, oracle):
+    o = oracle_basis(oracle, 1000, 200)
+    omg, x, y, terms, rng = make_problem(spec, 1000, 200)
+    obg = spec.outerbase(omg, x)
+    a, r = rng.normal(size=200), rng.normal(size=1000)
+    ob = o["ob"]
+    assert relerr(obg.sqmm(terms, a), ob.sqmm(terms, a)) < 1e-9
+    assert relerr(obg.sqtmm(terms, r), ob.sqtmm(terms, r)) < 1e-9
+    assert relerr(obg.sqcolsums(terms), ob.sqcolsums(terms)) < 1e-9
+    assert obg.spec_state(terms) == 1
+
+
+def test_spec_loglik_and_optcg(spec, oracle):
+    """loglik_gauss::update / hessmult (fused epilogues of phi_a_spec) and lpdf::optcg on the
+    specialised kernels: same iteration count, coefficients and log-density within 1e-8."""
+    N, K = 10000, 1000
+    O = _lpdf_pair(oracle, N, K, "prior_first")
+    G = _lpdf_pair(spec, N, K, "prior_first")
+    rng = O[4]
+    coeff = rng.normal(size=K) / 100
+    g = rng.normal(size=K)
+    for T in (O, G):
+        T[6].updatepara([np.log(0.1)])
+        T[6].update(coeff)
+    lo, lg = O[6], G[6]
+    assert abs(lg.val - lo.val) <= 1e-8 * abs(lo.val)
+    assert relerr(lg.grad, lo.grad) < 1e-8
+    assert relerr(lg.yhat, lo.yhat) < 1e-9
+    assert relerr(lg.hessmult(g), lo.hessmult(g)) < 1e-8
+    assert relerr(lg.diaghess(), lo.diaghess()) < 1e-8
+    for T in (O, G):
+        T[7].domarg = True
+        T[7].optcg(0.001, 100)
+    vo, vg = O[7], G[7]
+    assert vg.cg_iters == vo.cg_iters
+    assert abs(vg.val - vo.val) <= 1e-8 * abs(vo.val)
+    assert relerr(vg.coeff, vo.coeff) < 1e-8
+
+
+def test_spec_full_size_properties(spec):
+    """BASELINE config 3 shape on the specialised kernels: linearity, adjointness, row-block
+    additivity, determinism (size-independent identities, no oracle)."""
+    rng = np.random.default_rng(11)
+    d, N, K = 10, 1_000_000, 2000
+    x = np.asfortranarray(rng.uniform(size=(N, d)))
+    om = spec.outermod()
+    om.setcovfs(["mat25pow"] * d)
+    q = np.linspace(0, 1, 40) * 40 / 41 + 0.5 / 41
+    om.setknot([np.quantile(x[:100000, l], q) for l in range(d)])
+    hyp = om.gethyp(); hyp[0::2] = np.linspace(-0.6, 0.4, d); om.updatehyp(hyp)
+    terms = om.selectterms(K)
+    ob = spec.outerbase(om, x, dograd=False)
+    a1, a2 = rng.normal(size=K), rng.normal(size=K)
+    r = rng.normal(size=N)
+    y1, y2 = ob.matmul(terms, a1), ob.matmul(terms, a2)
+    assert ob.spec_state(terms) == 1
+    assert relerr(ob.matmul(terms, 2.0 * a1 - 3.0 * a2), 2.0 * y1 - 3.0 * y2) < 1e-12
+    lhs, rhs = float(y1 @ r), float(a1 @ ob.tmatmul(terms, r))
+    assert abs(lhs - rhs) <= 1e-11 * (np.abs(y1) @ np.abs(r))
+    t1 = ob.tmatmul(terms, r)
+    np.testing.assert_array_equal(t1, ob.tmatmul(terms, r))
+    half = N // 2
+    obA, obB = spec.outerbase(om, x[:half], dograd=False), spec.outerbase(om, x[half:], dograd=False)
+    assert relerr(obA.tmatmul(terms, r[:half]) + obB.tmatmul(terms, r[half:]), t1) < 1e-12
+    # against the interpreter kernels on the same object
+    spec.set_option("spec", 0)
+    assert relerr(ob.matmul(terms, a1), y1) < 1e-13
+    assert relerr(ob.tmatmul(terms, r), t1) < 1e-12
