@@ -174,8 +174,8 @@ int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
 int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
 /* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */
 int ob_outerbase_spec_state(ob_outerbase* ob, const uint64_t* terms, uint64_t K, int* state);
-/* Test hook (no GPU needed): the CUDA source the generator emits for a table.  opts9 = {wa, ra,
- * pa, cache_a, wt, rt, pt, cache_t, acc_cap} or NULL for the defaults.  Call with buf = NULL to
+/* Test hook (no GPU needed): the CUDA source the generator emits for a table.  opts9 = {ra, qa,
+ * tga, cache_a, wt, rt, pt, cache_t, acc_cap} or NULL for the defaults.  Call with buf = NULL to
  * get the length; info = {types, accumulators per thread, tile rows Phi a, tile rows Phi^T}. */
 int ob_spec_source(const uint64_t* terms, uint64_t K, uint64_t d, const int* opts9, char* buf,
                    uint64_t* len, uint64_t* info /* 4 */);

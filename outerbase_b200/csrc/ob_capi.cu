@@ -264,10 +264,10 @@ int ob_spec_source(const uint64_t* terms, uint64_t K, uint64_t d, const int* opt
   OB_TRY
   need(terms, "terms"); need(len, "len");
   obs::SpecOptions o = obd::spec_default_options();
-  if (opts9) { o.wa = opts9[0]; o.ra = opts9[1]; o.pa = opts9[2]; o.cache_a = opts9[3]; o.wt = opts9[4]; o.rt = opts9[5]; o.pt = opts9[6]; o.cache_t = opts9[7]; o.acc_cap = opts9[8]; }
+  if (opts9) { o.ra = opts9[0]; o.qa = opts9[1]; o.tga = opts9[2]; o.cache_a = opts9[3]; o.wt = opts9[4]; o.rt = opts9[5]; o.pt = opts9[6]; o.cache_t = opts9[7]; o.acc_cap = opts9[8]; }
   const int types = obs::choose_types(terms, K, d, o);
   if (!types) throw std::invalid_argument("terms table is not trie-compilable");
-  const obt::Program pa = obt::compile(terms, K, d, o.wa), pt = obt::compile(terms, K, d, types * o.wt);
+  const obt::Program pa = obt::compile(terms, K, d, 1), pt = obt::compile(terms, K, d, types * o.wt);
   const obs::SpecSource S = obs::generate(&pa, &pt, types, o);
   if (!S.ok) throw std::invalid_argument(S.why);
   if (info) { info[0] = (u64)S.types; info[1] = (u64)S.nacc; info[2] = (u64)S.tr_a; info[3] = (u64)S.tr_t; }

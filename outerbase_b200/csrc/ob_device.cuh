@@ -152,6 +152,7 @@ void launch_phi_t_reduce(Ctx& c, const double* partial, int nblocks, int nslots,
 struct SpecKernels;
 bool spec_compiler_available();
 obs::SpecOptions spec_default_options();
+obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, size_t nslots);
 /* pa: program with G = opt.wa, pt: G = types * opt.wt.  only_if_cached: return null instead of compiling */
 std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const obt::Program& pt, int types, const obs::SpecOptions& opt,
                                         bool only_if_cached);

@@ -61,6 +61,7 @@ struct OuterBase {
     std::unique_ptr<obd::DevProgram> pa, pt;
     std::shared_ptr<obd::SpecKernels> k;
     int types = 0;
+    obs::SpecOptions opt;
     int state = 0;      /* 0 interpreter so far, 1 module ready, -1 not specialisable */
     bool probed = false; /* disk cache looked up */
     double work = 0;    /* row-terms sent through the interpreter kernels */
@@ -144,9 +145,9 @@ struct OuterBase {
     om_version = om->version;
   }
 
-  /* the program a Phi kernel runs.  dir 0 = Phi a, 1 = Phi^T.  Measured at C3 (profiles/): Phi a is
-   * fastest on the shared-memory kernel (16 term groups), Phi^T on the TMEM kernel (4 term groups);
-   * OB_PHI=v1|v2 forces one generation for both. */
+  /* the program an INTERPRETER Phi kernel runs (dir 0 = Phi a, 1 = Phi^T): the shared-memory kernels
+   * with 16 term groups; OB_PHI=v2 opts into the TMEM-resident interpreter (4 term groups).  Tables that
+   * prove hot run on the terms-specialised kernels instead (spec_for). */
   obd::DevProgram* program(const u64* terms, u64 K, int aug, int dir = 0) {
     if (obd::tmem_kernels_enabled(dir)) {
       obd::DevProgram* p4 = program_g(terms, K, aug, 4, 512 / (2 * obd::tmem_rows_per_lane(ctx, N)));
@@ -209,18 +210,20 @@ struct OuterBase {
     const bool probe = !e->probed && (double)N * (double)K >= 1e8; /* large tables: a cached module is free */
     if (!now && !hot && !probe) return nullptr;
     try {
-      const obs::SpecOptions opt = obd::spec_default_options();
       if (!e->pa) {
-        e->types = obs::choose_types(terms, K, d, opt);
-        if (e->types == 0) throw std::runtime_error("not a trie-compilable table (duplicate or too deep terms)");
         e->pa.reset(new obd::DevProgram());
-        e->pa->host = obt::compile(terms, K, d, opt.wa);
+        e->pa->host = obt::compile(terms, K, d, 1);
+        if (!e->pa->host.fast_ok) throw std::runtime_error("not a trie-compilable table (duplicate or too deep terms)");
+        e->opt = obd::spec_adapt_options(ctx, obd::spec_default_options(), (int)e->pa->host.cols.size(), e->pa->host.nslots());
+        e->types = obs::choose_types(terms, K, d, e->opt);
+        if (e->types == 0) throw std::runtime_error("not a trie-compilable table (duplicate or too deep terms)");
         e->pt.reset(new obd::DevProgram());
-        e->pt->host = obt::compile(terms, K, d, e->types * opt.wt);
+        e->pt->host = obt::compile(terms, K, d, e->types * e->opt.wt);
         e->pa->upload(ctx.stream);
         e->pt->upload(ctx.stream);
         ctx.sync();
       }
+      const obs::SpecOptions& opt = e->opt;
       e->probed = true;
       e->k = obd::spec_build(ctx, e->pa->host, e->pt->host, e->types, opt, /*only_if_cached=*/!(now || hot));
       if (!e->k) return nullptr; /* not in the cache: stay on the interpreter until hot */

@@ -881,12 +881,13 @@ static void set_smem(Kern k, size_t bytes) {
 
 /* ---- second generation (TMEM) geometry */
 bool tmem_kernels_enabled(int dir) {
-  static int mode = -1; /* 0 auto, 1 v1 only, 2 v2 for both */
+  static int mode = -1; /* 0 default = v1 (shared-memory interpreter), 1 v1 only, 2 v2 (TMEM interpreter) for both */
   if (mode < 0) {
     const char* e = getenv("OB_PHI");
     mode = !e ? 0 : (std::string(e) == "v1" ? 1 : (std::string(e) == "v2" ? 2 : 0));
   }
-  return mode == 2 || (mode == 0 && dir == 1);
+  (void)dir; /* large problems run on the terms-specialised kernels (ob_spec.hpp); v2 is opt-in (OB_PHI=v2) */
+  return mode == 2;
 }
 bool tmem_eligible(const obt::Program& P) { return P.fast_ok && P.G == 4 && P.fwd_stack <= 4 && P.bwd_stack <= 4; }
 

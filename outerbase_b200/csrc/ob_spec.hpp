@@ -41,21 +41,29 @@ struct SpecParams {
   const int* slot_term;
   double sd;
   unsigned long long N;
-  int ncol, has_ops, sq, mode, ntiles, nbuf, nslots;
-  unsigned off_tile, tile_doubles, off_part, off_vec;
+  int ncol, has_ops, sq, mode, ntiles, nstage, nslots;
+  unsigned off_tile, tile_doubles, off_vec;
 };
 
 struct SpecOptions {
-  /* Phi a: streams, rows per lane, passes per tile, register-cached columns per stream, row groups
-   * (compute warps = wa * qa) */
-  int wa = 2, ra = 1, pa = 4, cache_a = 60, qa = 4;
-  /* Phi^T: warps per CTA, rows per lane, passes per tile, cached columns, accumulators per warp (cap) */
-  int wt = 12, rt = 1, pt = 4, cache_t = 20, acc_cap = 44;
+  /* Phi a (one stream = the whole program): rows per lane, passes per tile (= warps per tile), tiles
+   * in work at once (compute warps = qa * tga), register-cached columns */
+  int ra = 1, qa = 4, tga = 2, cache_a = 60;
+  /* Phi^T: warps per CTA (= streams per CTA type), rows per lane, passes per tile, cached columns,
+   * accumulators per warp (cap) */
+  int wt = 6, rt = 1, pt = 4, cache_t = 16, acc_cap = 112;
+  /* producer warps of both kernels (one warp issues one bulk copy per ~100 cycles, tools/tma_bench.cu) */
+  int np = 2;
+  /* Phi^T: 1 = form a cluster of the CTA types and multicast the tile (when 2 <= types <= 8, np >= 2).
+   * Correct but measured 2-3x slower than L2-served repeats on B200 (profiles/r01_spec_sweeps.txt): off. */
+  int mc = 0;
 };
 
 struct SpecSource {
   std::string src;
   int types = 0, nacc = 0; /* Phi^T: CTA types, accumulators declared per thread */
+  int maxcols_t = 0;       /* Phi^T: most columns any type stages */
+  int cluster = 1;         /* Phi^T: CTAs per cluster (= types when multicasting, else 1) */
   int tr_a = 0, tr_t = 0;  /* rows per tile */
   SpecOptions opt;
   bool ok = false;
@@ -76,9 +84,13 @@ struct Emitter {
 struct Factors {
   std::vector<int> cached; /* -1 / 1 per column */
   std::vector<char> declared;
+  std::vector<int> pos;    /* program column -> column of the staged tile */
   int R, TR;
-  Factors(const Program& P, const std::vector<uint32_t>& words, uint32_t lo, uint32_t hi, bool fwd, int cache, int R_, int TR_)
+  Factors(const Program& P, const std::vector<uint32_t>& words, uint32_t lo, uint32_t hi, bool fwd, int cache, int R_, int TR_,
+          const std::vector<int>* pos_ = nullptr)
       : R(R_), TR(TR_) {
+    if (pos_) pos = *pos_;
+    else { pos.resize(P.cols.size()); for (size_t i = 0; i < pos.size(); ++i) pos[i] = (int)i; }
     const size_t nc = P.cols.size();
     std::vector<int> use(nc, 0);
     for (uint32_t i = lo; i < hi; ++i) {
@@ -97,11 +109,11 @@ struct Factors {
   /* expression for factor (col, r); may first emit the declaration of a cached column */
   std::string get(Emitter& e, int col, int r) {
     char b[96];
-    const unsigned off = (unsigned)(col * TR + 32 * r) * 8u;
+    const unsigned off = (unsigned)(pos[col] * TR + 32 * r) * 8u;
     if (!cached[col]) { std::snprintf(b, sizeof b, "ldv(tp + %uu)", off); return b; }
     if (!declared[col]) {
       declared[col] = 1;
-      for (int q = 0; q < R; ++q) e.f("const double f%d_%d = lds(tp + %uu);\n", col, q, (unsigned)(col * TR + 32 * q) * 8u);
+      for (int q = 0; q < R; ++q) e.f("const double f%d_%d = lds(tp + %uu);\n", col, q, (unsigned)(pos[col] * TR + 32 * q) * 8u);
     }
     std::snprintf(b, sizeof b, "f%d_%d", col, r);
     return b;
@@ -180,9 +192,9 @@ inline void emit_bwd(Emitter& e, const Program& P, int g, int R, int TR, int cac
 }
 
 /* forward (top-down) stream g -> statements accumulating into acc<i>; returns the emit count */
-inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cache) {
+inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cache, const std::vector<int>& pos) {
   using namespace obt;
-  Factors F(P, P.fwd, P.fwd_off[g], P.fwd_off[g + 1], true, cache, R, TR);
+  Factors F(P, P.fwd, P.fwd_off[g], P.fwd_off[g + 1], true, cache, R, TR, &pos);
   int nv = 0, ia = 0;
   std::string cur = "b", stk[kMaxDepth + 2];
   stk[0] = "b";
@@ -255,39 +267,35 @@ inline int choose_types(const u64* terms, u64 K, u64 d, const SpecOptions& opt) 
   return 0;
 }
 
-/* pa: program compiled with G = opt.wa (or null: no Phi a kernel); pt: G = types * opt.wt (or null) */
+/* pa: program compiled with G = 1 (or null: no Phi a kernel); pt: G = types * opt.wt (or null) */
 inline SpecSource generate(const Program* pa, const Program* pt, int types, const SpecOptions& opt) {
   using namespace detail;
   SpecSource S;
   S.opt = opt;
-  S.tr_a = 32 * opt.ra * opt.pa;
+  S.tr_a = 32 * opt.ra * opt.qa;
   S.tr_t = 32 * opt.rt * opt.pt;
   const bool want_a = pa != nullptr, want_t = pt != nullptr;
   if (!want_a && !want_t) { S.why = "nothing to generate"; return S; }
   const u64 K = want_a ? pa->K : pt->K;
   if (K == 0) { S.why = "no terms"; return S; }
-  if (256 % S.tr_a || 256 % S.tr_t || S.tr_a > 32 * opt.wa * opt.qa || opt.pa % opt.qa || opt.wa * opt.qa > 31) {
+  if (256 % S.tr_a || 256 % S.tr_t || opt.np < 1 || opt.np > 8 || opt.qa * opt.tga + opt.np > 32 || opt.wt + opt.np > 32 || opt.qa < 1 || opt.tga < 1 || opt.tga > 8 || opt.wt > 31) {
     S.why = "inconsistent tile options";
     return S;
   }
-  if ((want_a && (!pa->fast_ok || pa->G != opt.wa || pa->tmem_cap)) || (want_t && (!pt->fast_ok || pt->G != types * opt.wt || pt->tmem_cap))) {
+  if ((want_a && (!pa->fast_ok || pa->G != 1 || pa->tmem_cap)) || (want_t && (!pt->fast_ok || pt->G != types * opt.wt || pt->tmem_cap))) {
     S.why = "programs do not match the options";
     return S;
   }
   Emitter hdr, tab, ca, ct, decl, red;
-  hdr.f("#define OBS_PARAM_BYTES %d\n#define OBS_K %llu\n", (int)sizeof(SpecParams), (unsigned long long)K);
+  hdr.f("#define OBS_PARAM_BYTES %d\n#define OBS_K %llu\n#define OBS_NP %d\n", (int)sizeof(SpecParams), (unsigned long long)K, opt.np);
   if (want_a) {
     const Program& P = *pa;
-    hdr.f("#define OBS_HAVE_A 1\n#define OBS_WA %d\n#define OBS_RA %d\n#define OBS_PA %d\n#define OBS_QA %d\n#define OBS_NCOLS_A %d\n",
-          opt.wa, opt.ra, opt.pa, opt.qa, (int)P.cols.size());
+    hdr.f("#define OBS_HAVE_A 1\n#define OBS_RA %d\n#define OBS_QA %d\n#define OBS_TGA %d\n#define OBS_NCOLS_A %d\n", opt.ra, opt.qa,
+          opt.tga, (int)P.cols.size());
     tab.f("__device__ const unsigned short obs_cols_a[] = {");
     for (size_t c = 0; c < P.cols.size(); ++c) tab.f("%d,", (int)c);
     tab.f("0};\n");
-    for (int g = 0; g < opt.wa; ++g) {
-      ca.f("case %d: {\n", g);
-      emit_bwd(ca, P, g, opt.ra, S.tr_a, opt.cache_a);
-      ca.f("} break;\n");
-    }
+    emit_bwd(ca, P, 0, opt.ra, S.tr_a, opt.cache_a);
   }
   if (want_t) {
     const Program& P = *pt;
@@ -309,9 +317,15 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
       auto& tc = tcols[g / opt.wt];
       for (size_t c = 0; c < used.size(); ++c) if (used[c] && std::find(tc.begin(), tc.end(), (int)c) == tc.end()) tc.push_back((int)c);
     }
+    S.cluster = (opt.mc && types >= 2 && types <= 8 && opt.np >= 2) ? types : 1;
     size_t maxcols = 1;
     for (auto& tc : tcols) maxcols = std::max(maxcols, tc.size());
-    hdr.f("#define OBS_NQ_T %d\n", (int)std::max<size_t>(1, (maxcols + 31) / 32));
+    if (S.cluster > 1) maxcols = P.cols.size(); /* multicast: every CTA receives every column */
+    hdr.f("#define OBS_CL %d\n", S.cluster);
+    tab.f("__device__ const unsigned short obs_cols_all[] = {");
+    for (size_t c = 0; c < P.cols.size(); ++c) tab.f("%d,", (int)c);
+    tab.f("0};\n");
+    hdr.f("#define OBS_MAXCOLS_T %d\n", (int)maxcols);
     tab.f("__device__ const unsigned short obs_cols_t[] = {");
     std::vector<int> coff{0};
     for (auto& tc : tcols) { std::sort(tc.begin(), tc.end()); for (int c : tc) tab.f("%d,", c); coff.push_back(coff.back() + (int)tc.size()); }
@@ -322,11 +336,16 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
     tab.f("};\n__device__ const unsigned short obs_slot_real[] = {");
     for (int g = 0; g < G; ++g) tab.f("%u,", P.slot_real[g]);
     tab.f("};\n");
+    S.maxcols_t = (int)maxcols;
     for (int g = 0; g < G; ++g) {
-      ct.f("case %d: {\n", g);
-      const int n = emit_fwd(ct, P, g, opt.rt, S.tr_t, opt.cache_t);
+      const auto& tc = tcols[g / opt.wt]; /* sorted above */
+      std::vector<int> pos(P.cols.size(), -1);
+      for (size_t i = 0; i < tc.size(); ++i) pos[tc[i]] = (int)i;
+      if (S.cluster > 1) for (size_t c = 0; c < pos.size(); ++c) pos[c] = (int)c;
+      ct.f("case %d: {\nOBS_T_LOOP_BEGIN\n", g);
+      const int n = emit_fwd(ct, P, g, opt.rt, S.tr_t, opt.cache_t, pos);
       if (n != (int)P.slot_real[g]) { S.why = "emit count mismatch"; return S; }
-      ct.f("} break;\n");
+      ct.f("OBS_T_LOOP_END\n} break;\n");
     }
     for (int i = 0; i < S.nacc; ++i) decl.f("  double acc%d = 0.0;\n", i);
     /* one butterfly per accumulator, once per launch; lane 0 stores */
@@ -338,7 +357,7 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
   }
   std::string body = scaffold_text();
   replace_marker(body, "//@@TABLES@@", tab.s);
-  if (want_a) replace_marker(body, "//@@CASES_A@@", ca.s);
+  if (want_a) replace_marker(body, "//@@BODY_A@@", ca.s);
   if (want_t) {
     replace_marker(body, "//@@ACC_DECL@@", decl.s);
     replace_marker(body, "//@@CASES_T@@", ct.s);

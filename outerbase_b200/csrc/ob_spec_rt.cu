@@ -129,9 +129,10 @@ struct SpecKernels {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t ka = nullptr, kt = nullptr;
   obs::SpecOptions opt;
-  int types = 0, tr_a = 0, tr_t = 0;
+  int types = 0, tr_a = 0, tr_t = 0, maxcols_t = 0, cluster = 1;
   size_t vec_bytes_a = 0; /* shared-memory copy of the coefficients, slot order */
   size_t smem_a_set = 0, smem_t_set = 0;
+  int max_clusters = 0;
   double compile_seconds = 0;
   bool from_cache = false;
   ~SpecKernels() { if (lib) cudaLibraryUnload(lib); }
@@ -139,10 +140,10 @@ struct SpecKernels {
 
 obs::SpecOptions spec_default_options() {
   obs::SpecOptions o;
-  if (const char* e = getenv("OB_SPEC_OPTS")) { /* wa,ra,pa,cache_a,wt,rt,pt,cache_t,acc_cap,qa -- tuning only */
-    int* f[] = {&o.wa, &o.ra, &o.pa, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.qa};
+  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc -- tuning only */
+    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc};
     int i = 0;
-    for (const char* p = e; *p && i < 10; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (const char* p = e; *p && i < 11; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
   }
   return o;
 }
@@ -152,7 +153,7 @@ std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const ob
   obs::SpecSource S = obs::generate(&pa, &pt, types, opt);
   if (!S.ok) throw std::runtime_error("specialised kernel generation failed: " + S.why);
   auto k = std::make_shared<SpecKernels>();
-  k->opt = opt; k->types = types; k->tr_a = S.tr_a; k->tr_t = S.tr_t;
+  k->opt = opt; k->types = types; k->tr_a = S.tr_a; k->tr_t = S.tr_t; k->maxcols_t = S.maxcols_t; k->cluster = S.cluster;
   k->vec_bytes_a = ((pa.nslots() * sizeof(double) + 127) / 128) * 128;
   const std::string cubin = spec_compile_source(S.src, &k->compile_seconds, &k->from_cache, only_if_cached);
   if (cubin.empty()) return nullptr;
@@ -172,42 +173,78 @@ static void spec_fill(obs::SpecParams& p, const PhiPlan& pl, int TR) {
   p.ntiles = (int)((pl.N + TR - 1) / TR);
 }
 
-static void spec_launch(Ctx& c, cudaKernel_t kern, size_t& smem_set, int grid, int threads, size_t smem, obs::SpecParams& p, const char* what) {
+static void spec_launch(Ctx& c, cudaKernel_t kern, size_t& smem_set, int grid, int threads, size_t smem, obs::SpecParams& p, const char* what,
+                        int cluster = 1) {
   if (smem > smem_set) {
     OB_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   void* args[] = {&p};
-  const cudaError_t e = cudaLaunchKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, c.stream);
+  cudaError_t e;
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = c.stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = cluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+  } else e = cudaLaunchKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, c.stream);
   if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
   c.launches++;
 }
 
+/* shared-memory layout: 16 mbarriers | coefficient copy (Phi a) | nstage tiles of (ncol + extra) columns */
+struct SpecGeom { int nstage = 0; unsigned off_vec = 0, off_tile = 0, tile_doubles = 0; size_t smem = 0; };
+static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t vec_bytes, int want_stages) {
+  SpecGeom g;
+  g.off_vec = 128;
+  g.off_tile = (unsigned)(128 + vec_bytes);
+  g.tile_doubles = (unsigned)((ncol + nextra) * TR);
+  const size_t tile_bytes = (size_t)g.tile_doubles * 8;
+  const size_t room = c.smem_optin > g.off_tile ? c.smem_optin - g.off_tile : 0;
+  g.nstage = (int)std::min<size_t>({(size_t)want_stages, room / std::max<size_t>(tile_bytes, 1), (size_t)8});
+  g.smem = g.off_tile + (size_t)g.nstage * tile_bytes;
+  return g;
+}
+
+/* shrink the tile geometry until a table with `ncol` columns and `nslots` coefficient slots fits the
+ * shared memory of the SM: fewer tiles in work first, then fewer rows per tile */
+obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, size_t nslots) {
+  for (;;) {
+    const size_t vec = std::max<size_t>(((nslots * 8 + 127) / 128) * 128, 8 * 32 * (size_t)(o.qa * o.tga + o.np));
+    if (spec_geometry(c, ncol, 1, 32 * o.ra * o.qa, vec, 8).nstage >= o.tga) break;
+    if (o.tga > 1) --o.tga;
+    else if (o.qa > 1) o.qa /= 2;
+    else if (o.ra > 1) o.ra /= 2;
+    else break;
+  }
+  while (spec_geometry(c, ncol, 2, 32 * o.rt * o.pt, 0, 8).nstage < 2 && o.pt > 1) o.pt /= 2;
+  return o;
+}
+
 bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol) {
-  const size_t a1 = 128 + (size_t)ncol * k.tr_a * 8 + 2 * (size_t)k.opt.wa * k.tr_a * 8 + k.vec_bytes_a;
-  const size_t t1 = 128 + (size_t)ncol * k.tr_t * 8 + 2 * (size_t)k.tr_t * 8;
-  return a1 <= c.smem_optin && t1 <= c.smem_optin;
+  /* a consumer group must never be a whole round of stages ahead of the producer (mbarrier parity
+   * would alias): tiles in work at once <= stages */
+  return spec_geometry(c, ncol, 1, k.tr_a, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (k.opt.qa * k.opt.tga + k.opt.np)), 8).nstage >= k.opt.tga &&
+         spec_geometry(c, k.maxcols_t, 2, k.tr_t, 0, 8).nstage >= 1;
 }
 
 void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs& a, Workspace& ws, int* grid_out) {
   if (pl.N == 0) { if (grid_out) *grid_out = 0; return; }
   if (pl.cols->nload != pl.cols->ncol) throw std::logic_error("specialised kernels take plain column tables only");
-  const int TR = k.tr_a;
+  const int TR = k.tr_a, warps = k.opt.qa * k.opt.tga;
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
-  p.tile_doubles = (unsigned)(p.ncol * TR);
-  const size_t tile_bytes = (size_t)p.tile_doubles * 8, part_bytes = 2 * (size_t)k.opt.wa * TR * 8;
-  p.nbuf = (128 + 2 * tile_bytes + part_bytes + k.vec_bytes_a <= c.smem_optin) ? 2 : 1;
-  p.off_tile = 128;
-  p.off_part = (unsigned)(128 + p.nbuf * tile_bytes);
-  p.off_vec = (unsigned)(p.off_part + part_bytes);
-  const size_t smem = p.off_vec + k.vec_bytes_a;
-  if (smem > c.smem_optin) throw std::logic_error("specialised Phi a does not fit in shared memory");
+  /* the coefficient copy doubles as the scratch of the final residual reduction (one double per thread) */
+  const SpecGeom g = spec_geometry(c, p.ncol, 1, TR, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (warps + k.opt.np)), k.opt.tga + 2);
+  if (g.nstage < k.opt.tga) throw std::logic_error("specialised Phi a does not fit in shared memory");
+  p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles;
   p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
   const int grid = std::max(1, std::min(p.ntiles, c.sms));
   if (a.mode == PHI_UPDATE) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
   p.a = a.a; p.slot_term = pl.prog->slot_term.p; p.nslots = (int)pl.prog->host.nslots();
-  spec_launch(c, k.ka, k.smem_a_set, grid, 32 * (k.opt.wa * k.opt.qa + 1), smem, p, "phi_a_spec");
+  spec_launch(c, k.ka, k.smem_a_set, grid, 32 * (warps + k.opt.np), g.smem, p, "phi_a_spec");
   if (grid_out) *grid_out = grid;
 }
 
@@ -220,19 +257,35 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   const int TR = k.tr_t;
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
-  p.tile_doubles = (unsigned)(p.ncol * TR);
-  const size_t tile_bytes = (size_t)p.tile_doubles * 8, b_bytes = 2 * (size_t)TR * 8;
-  p.nbuf = (128 + 2 * tile_bytes + b_bytes <= c.smem_optin) ? 2 : 1;
-  p.off_tile = 128;
-  p.off_part = (unsigned)(128 + p.nbuf * tile_bytes);
-  const size_t smem = p.off_part + b_bytes;
-  if (smem > c.smem_optin) throw std::logic_error("specialised Phi^T does not fit in shared memory");
-  const int J = std::max(1, std::min(p.ntiles, c.sms / k.types));
+  const SpecGeom g = spec_geometry(c, k.maxcols_t, 2, TR, 0, 4);
+  if (g.nstage < 1) throw std::logic_error("specialised Phi^T does not fit in shared memory");
+  p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles;
+  int jmax = c.sms / k.types;
+  if (k.cluster > 1) { /* clusters that can be resident at once: a second, partial wave would double the time */
+    if (k.max_clusters == 0 || g.smem > k.smem_t_set) {
+      if (g.smem > k.smem_t_set) {
+        OB_CUDA(cudaFuncSetAttribute((const void*)k.kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        k.smem_t_set = g.smem;
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(c.sms / k.cluster * k.cluster); cfg.blockDim = dim3(32 * (k.opt.wt + k.opt.np)); cfg.dynamicSmemBytes = g.smem;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = k.cluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int nc = 0;
+      OB_CUDA(cudaOccupancyMaxActiveClusters(&nc, (const void*)k.kt, &cfg));
+      if (nc < 1) throw std::logic_error("the Phi^T cluster does not fit on this GPU");
+      k.max_clusters = nc;
+    }
+    jmax = std::min(jmax, k.max_clusters);
+  }
+  const int J = std::max(1, std::min(p.ntiles, jmax));
   const int grid = J * k.types;
   p.win = w;
   p.nslots = (int)pr.host.nslots();
   p.partial = ws.partial.ensure((size_t)J * p.nslots);
-  spec_launch(c, k.kt, k.smem_t_set, grid, 32 * (k.opt.wt + 1), smem, p, "phi_t_spec");
+  spec_launch(c, k.kt, k.smem_t_set, grid, 32 * (k.opt.wt + k.opt.np), g.smem, p, "phi_t_spec", k.cluster);
   launch_phi_t_reduce(c, p.partial, J, p.nslots, pr.slot_term.p, out);
 }
 

@@ -1,6 +1,6 @@
 /* spec_probe -- offline check of the terms-specialised kernels: generate the source for a
  * terms table, compile it with NVRTC for sm_100a (no GPU needed) and report ptxas' resource
- * usage.  usage: spec_probe terms.bin out_prefix [wa ra pa cache_a wt rt pt cache_t acc_cap]
+ * usage.  usage: spec_probe terms.bin out_prefix [ra qa tga cache_a wt rt pt cache_t acc_cap]
  * terms.bin = u64 K, u64 d, then K*d u64 column-major. */
 #include <nvrtc.h>
 
@@ -20,12 +20,12 @@ int main(int argc, char** argv) {
   std::vector<uint64_t> terms(K * d);
   in.read((char*)terms.data(), K * d * 8);
   obs::SpecOptions o;
-  int* f[] = {&o.wa, &o.ra, &o.pa, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.qa};
-  for (int i = 0; i < 10 && 3 + i < argc; ++i) *f[i] = std::atoi(argv[3 + i]);
+  int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc};
+  for (int i = 0; i < 11 && 3 + i < argc; ++i) *f[i] = std::atoi(argv[3 + i]);
   auto t0 = std::chrono::steady_clock::now();
   const int types = obs::choose_types(terms.data(), K, d, o);
   if (!types) { std::fprintf(stderr, "terms table is not trie-compilable\n"); return 1; }
-  const obt::Program pa = obt::compile(terms.data(), K, d, o.wa), pt = obt::compile(terms.data(), K, d, types * o.wt);
+  const obt::Program pa = obt::compile(terms.data(), K, d, 1), pt = obt::compile(terms.data(), K, d, types * o.wt);
   obs::SpecSource S = obs::generate(&pa, &pt, types, o);
   auto t1 = std::chrono::steady_clock::now();
   if (!S.ok) { std::fprintf(stderr, "generate failed: %s\n", S.why.c_str()); return 1; }

@@ -4,8 +4,12 @@ import json, os, subprocess, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for cfg in sys.argv[1:]:
     env = dict(os.environ, OB_SPEC_OPTS=cfg)
-    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "6", "--warmup", "3", "--no-optcg", "--no-cpu-baseline"],
-                       env=env, capture_output=True, text=True)
+    try:
+      p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "6", "--warmup", "3", "--no-optcg", "--no-cpu-baseline"],
+                       env=env, capture_output=True, text=True, timeout=120)
+    except subprocess.TimeoutExpired:
+      print(cfg, "TIMEOUT", flush=True)
+      continue
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])
         print(cfg, "pairs/s %.1f" % d["value"], "phi_a %.3f ms" % d["roofline"]["ms_phi_a"], "phi_t %.3f ms" % d["roofline"]["ms_phi_t"], flush=True)
