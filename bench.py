@@ -157,7 +157,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 50_000
+    sample = 250_000
     val, cores, done, dt = cpu_pairs_per_s(sample, args.steps, args.warmup, budget_s=60.0)
     W, Lcols = None, None
     line = {
@@ -269,16 +269,27 @@ def main():
     ms, t_a, t_t = [float(v) for v in tms.cpu()]
     value = 2 * args.steps / (ms * 1e-3)
 
-    # ---- e2e: reference-facing calls with host buffers, pinned staging inside the library
+    # ---- e2e: the reference-facing calls outerbase::mm / outerbase::tmm with HOST buffers, every call
+    # copying its inputs in and its result out (pinned host memory on both sides, as the contract asks)
+    def pinned(n, src=None):
+        t = torch.empty(n, dtype=torch.float64).pin_memory()
+        v = t.numpy()
+        if src is not None:
+            v[:] = src
+        return t, v
+    _ka, a_p = pinned(K_TERMS, a_h)
+    _kr, r_p = pinned(nloc, r_h)
+    _ky, y_p = pinned(nloc)
+    _kg, g_p = pinned(K_TERMS)
     for _ in range(2):
-        ob.matmul(terms, a_h); ob.tmatmul(terms, r_h)
+        ob.matmul(terms, a_p, out=y_p); ob.tmatmul(terms, r_p, out=g_p)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(e2e_steps):
         for _ in range(2):
-            yh = ob.matmul(terms, a_h)
-            gh = ob.tmatmul(terms, r_h)
+            yh = ob.matmul(terms, a_p, out=y_p)
+            gh = ob.tmatmul(terms, r_p, out=g_p)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -331,8 +342,15 @@ def main():
         flop = nmax * (W + 1)
         achieved = flop / (t_dom * 1e-3) / 1e12
         bytes_alg = nmax * 8 * (Lcols + 1) + nmax * 8
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+        # `ncu --set full` capture of this exact workload (profiles/r01_spec_ncu_summary.md); other shapes: null
+        traffic, traffic_src = None, None
+        if args.spec == "1" and world == 1 and N == N_TOTAL:
+            traffic = {"phi_t_spec": 616.340e6 + 3.624e6, "phi_a_spec": 608.137e6 + 10.519e6}[dom]
+            traffic_src = "ncu --set full, profiles/r01_spec_ncu_summary.md (bytes per launch)"
         roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                    "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": "DFMA micro-benchmark run in this process (nominal 37.2 TFLOP/s at 1965 MHz)",
                     "algorithmic_flop_per_launch": flop, "W": W, "Lcols": Lcols,
                     "ms_phi_a": t_a, "ms_phi_t": t_t,
@@ -352,8 +370,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                sample = 20_000
-                v, cores, done, dtc = cpu_pairs_per_s(sample, 8, 1, budget_s=20.0)
+                sample = 250_000  # ~10-20 s of CPU work on the box's host cores
+                v, cores, done, dtc = cpu_pairs_per_s(sample, 40, 1, budget_s=15.0)
                 line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": int(cores), "kind": "port",
                                         "sample": f"{sample} of {N} rows, {done} steps of 2 pairs in {dtc:.1f} s, scaled by rows"}
             except Exception as e:  # the oracle is only the reported baseline

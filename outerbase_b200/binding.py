@@ -413,7 +413,7 @@ class outerbase(_Handle):
         self._lib.call("outerbase_getmat", self._h, _p(t), _u(t.shape[0]), _p(out))
         return out
 
-    def _mm(self, sq, terms, a):
+    def _mm(self, sq, terms, a, out=None):
         t, a = _terms(terms), _f64(a)
         if a.ndim == 2:
             out = np.empty((self.n_row, a.shape[1]), order="F")
@@ -421,11 +421,14 @@ class outerbase(_Handle):
             return out
         if a.size != t.shape[0]:
             raise ValueError("a must have one entry per term")
-        out = np.empty(self.n_row)
+        if out is None:
+            out = np.empty(self.n_row)
+        elif out.dtype != np.float64 or out.size != self.n_row or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 vector with one entry per row")
         self._lib.call("outerbase_mm", self._h, C.c_int(sq), _p(t), _u(t.shape[0]), _p(a), _p(out))
         return out
 
-    def _tmm(self, sq, terms, a):
+    def _tmm(self, sq, terms, a, out=None):
         t, a = _terms(terms), _f64(a)
         if a.shape[0] != self.n_row:
             raise ValueError("a must have one entry per row")
@@ -433,7 +436,10 @@ class outerbase(_Handle):
             out = np.empty((t.shape[0], a.shape[1]), order="F")
             self._lib.call("outerbase_tmm_mat", self._h, C.c_int(sq), _p(t), _u(t.shape[0]), _p(a), _u(a.shape[1]), _p(out))
             return out
-        out = np.empty(t.shape[0])
+        if out is None:
+            out = np.empty(t.shape[0])
+        elif out.dtype != np.float64 or out.size != t.shape[0] or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 vector with one entry per term")
         self._lib.call("outerbase_tmm", self._h, C.c_int(sq), _p(t), _u(t.shape[0]), _p(a), _p(out))
         return out
 
@@ -452,11 +458,12 @@ class outerbase(_Handle):
         return out, outge
 
     # R-visible methods (interfaceR.cpp:686-693)
-    def matmul(self, terms, a):
-        return self._mm(0, terms, a)
+    def matmul(self, terms, a, out=None):
+        """obj$matmul(terms, a); `out` (optional) receives the result in place, e.g. a pinned buffer."""
+        return self._mm(0, terms, a, out)
 
-    def tmatmul(self, terms, a):
-        return self._tmm(0, terms, a)
+    def tmatmul(self, terms, a, out=None):
+        return self._tmm(0, terms, a, out)
 
     def matmul_gradhyp(self, terms, a):
         return self._mmge(0, terms, a)[1]

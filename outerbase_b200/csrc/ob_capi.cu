@@ -266,7 +266,7 @@ int ob_spec_source(const uint64_t* terms, uint64_t K, uint64_t d, const int* opt
   obs::SpecOptions o = obd::spec_default_options();
   if (opts9) { o.ra = opts9[0]; o.qa = opts9[1]; o.tga = opts9[2]; o.cache_a = opts9[3]; o.wt = opts9[4]; o.rt = opts9[5]; o.pt = opts9[6]; o.cache_t = opts9[7]; o.acc_cap = opts9[8]; }
   const int types = obs::choose_types(terms, K, d, o);
-  if (!types) throw std::invalid_argument("terms table is not trie-compilable");
+  if (!types) throw std::invalid_argument("terms table is not trie-compilable (duplicate or too deep terms), or acc_cap is below one trie segment (32)");
   const obt::Program pa = obt::compile(terms, K, d, 1), pt = obt::compile(terms, K, d, types * o.wt);
   const obs::SpecSource S = obs::generate(&pa, &pt, types, o);
   if (!S.ok) throw std::invalid_argument(S.why);

@@ -253,7 +253,8 @@ inline const char* scaffold_text() {
 }
 
 /* Phi^T: smallest number of CTA types (streams = types * wt) whose busiest stream keeps its
- * accumulators within the cap.  0: the table is not trie-compilable. */
+ * accumulators within the cap.  0: the table is not trie-compilable, or the cap is below what one
+ * trie segment needs (ob_terms.hpp cuts segments of >= 24 nodes). */
 inline int choose_types(const u64* terms, u64 K, u64 d, const SpecOptions& opt) {
   if (K == 0) return 0;
   int types = (int)std::max<u64>(1, (K + (u64)opt.wt * opt.acc_cap - 1) / ((u64)opt.wt * opt.acc_cap));
@@ -295,7 +296,12 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
     tab.f("__device__ const unsigned short obs_cols_a[] = {");
     for (size_t c = 0; c < P.cols.size(); ++c) tab.f("%d,", (int)c);
     tab.f("0};\n");
+    /* machine-readable layout (comments): tile column -> (dimension, level), coefficient slot -> term */
+    for (size_t c = 0; c < P.cols.size(); ++c) tab.f("// OBS_LAYOUT_A %d %u %u\n", (int)c, P.cols[c].dim, P.cols[c].level);
+    for (u64 i = 0; i < P.nslots(); ++i) tab.f("// OBS_SLOT_A %d %d\n", (int)i, (int)P.slot_term[i]);
+    ca.f("/*BEGIN_BODY_A*/\n");
     emit_bwd(ca, P, 0, opt.ra, S.tr_a, opt.cache_a);
+    ca.f("/*END_BODY_A*/\n");
   }
   if (want_t) {
     const Program& P = *pt;
@@ -337,15 +343,23 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
     for (int g = 0; g < G; ++g) tab.f("%u,", P.slot_real[g]);
     tab.f("};\n");
     S.maxcols_t = (int)maxcols;
+    for (int t = 0; t < types; ++t) /* tile column of every type -> (dimension, level) */
+      for (size_t i = 0; i < (S.cluster > 1 ? P.cols.size() : tcols[t].size()); ++i) {
+        const int c = S.cluster > 1 ? (int)i : tcols[t][i];
+        tab.f("// OBS_LAYOUT_T %d %d %u %u\n", t, (int)i, P.cols[c].dim, P.cols[c].level);
+      }
     for (int g = 0; g < G; ++g) {
       const auto& tc = tcols[g / opt.wt]; /* sorted above */
       std::vector<int> pos(P.cols.size(), -1);
       for (size_t i = 0; i < tc.size(); ++i) pos[tc[i]] = (int)i;
       if (S.cluster > 1) for (size_t c = 0; c < pos.size(); ++c) pos[c] = (int)c;
-      ct.f("case %d: {\nOBS_T_LOOP_BEGIN\n", g);
+      tab.f("// OBS_STREAM_T %d type %d terms", g, g / opt.wt);
+      for (uint32_t i = 0; i < P.slot_real[g]; ++i) tab.f(" %d", (int)P.slot_term[P.slot_base[g] + i]);
+      tab.f("\n");
+      ct.f("case %d: {\nOBS_T_LOOP_BEGIN\n/*BEGIN_CASE_T %d*/\n", g, g);
       const int n = emit_fwd(ct, P, g, opt.rt, S.tr_t, opt.cache_t, pos);
       if (n != (int)P.slot_real[g]) { S.why = "emit count mismatch"; return S; }
-      ct.f("OBS_T_LOOP_END\n} break;\n");
+      ct.f("/*END_CASE_T*/\nOBS_T_LOOP_END\n} break;\n");
     }
     for (int i = 0; i < S.nacc; ++i) decl.f("  double acc%d = 0.0;\n", i);
     /* one butterfly per accumulator, once per launch; lane 0 stores */

@@ -1,0 +1,126 @@
+"""CPU tests of the kernel generator (outerbase_b200/csrc/ob_spec.hpp): the CUDA source it emits for
+a terms table (a) compiles for sm_100a with NVRTC -- no GPU needed -- and (b) computes the right
+numbers: the generated statements are lifted out of the source, compiled as HOST C++ with the three
+load helpers stubbed, run on one random row and compared with the definition
+Phi[n,k] = prod_{l: t_kl>0} B[n, l, t_kl] (src/linalg.cpp:70-75)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import make_problem
+
+
+def _terms(product_symbols, K, d=8):
+    om, x, y, terms, rng = make_problem(product_symbols, 50, K, d=d)
+    return np.asarray(terms), rng
+
+
+@pytest.mark.parametrize("K", [1, 7, 120])
+def test_generated_source_compiles_for_sm100a(product_symbols, K):
+    terms, _ = _terms(product_symbols, K)
+    src, info = product_symbols.spec_source(terms)
+    assert "phi_a_spec" in src and "phi_t_spec" in src and info["types"] >= 1
+    nbytes, seconds = product_symbols.spec_compile_check(src)
+    assert nbytes > 10_000
+
+
+def test_options_and_multicast_variant_compile(product_symbols):
+    terms, _ = _terms(product_symbols, 300)
+    # ra, qa, tga, cache_a, wt, rt, pt, cache_t, acc_cap [np, mc come from the defaults]
+    src, info = product_symbols.spec_source(terms, [2, 2, 2, 16, 8, 2, 2, 8, 32])
+    assert info["types"] >= 2 and info["tile_rows_a"] == 128 and info["tile_rows_t"] == 128
+    product_symbols.spec_compile_check(src)
+    with pytest.raises(ValueError):
+        product_symbols.spec_source(terms, [1, 3, 2, 16, 8, 1, 4, 8, 32])  # 96-row tiles do not divide the row padding
+
+
+HARNESS = r"""
+#include <cmath>
+#include <cstdint>
+static const double* TILE;
+static const double* AS;
+static inline double lds(uint32_t a) { return TILE[a / 8]; }
+static inline double ldv(uint32_t a) { return TILE[a / 8]; }
+template <int OFF> static inline double lda(uint32_t) { return AS[OFF / 8]; }
+template <int OFF> static inline void lda2(uint32_t, double& x, double& y) { x = AS[OFF / 8]; y = AS[OFF / 8 + 1]; }
+using std::fma;
+extern "C" void run_a(const double* tile, const double* as_, double* out) {
+  TILE = tile; AS = as_;
+  const uint32_t tp = 0, as = 0; (void)as;
+  double o[1] = {0.0};
+  {
+%(body_a)s
+  }
+  out[0] = o[0];
+}
+%(cases_t)s
+"""
+CASE_T = r"""
+extern "C" void run_t_%(g)d(const double* tile, double bval, double* accs) {
+  TILE = tile;
+  const uint32_t tp = 0;
+  double b[1] = {bval};
+%(decl)s
+  {
+%(body)s
+  }
+%(store)s
+}
+"""
+
+
+def test_generated_statements_compute_phi(product_symbols, tmp_path):
+    K, d = 160, 8
+    terms, rng = _terms(product_symbols, K, d)
+    opts = [1, 4, 2, 12, 3, 1, 4, 6, 32]  # small streams: several CTA types, cached and uncached columns both occur
+    src, info = product_symbols.spec_source(terms, opts)
+    TRA, TRT = info["tile_rows_a"], info["tile_rows_t"]
+    lay_a = [tuple(map(int, m)) for m in re.findall(r"// OBS_LAYOUT_A (\d+) (\d+) (\d+)", src)]
+    slot_a = [tuple(map(int, m)) for m in re.findall(r"// OBS_SLOT_A (\d+) (-?\d+)", src)]
+    lay_t = [tuple(map(int, m)) for m in re.findall(r"// OBS_LAYOUT_T (\d+) (\d+) (\d+) (\d+)", src)]
+    streams = {int(g): (int(t), [int(v) for v in rest.split()]) for g, t, rest in re.findall(r"// OBS_STREAM_T (\d+) type (\d+) terms([ \d-]*)", src)}
+    body_a = re.search(r"/\*BEGIN_BODY_A\*/(.*?)/\*END_BODY_A\*/", src, re.S).group(1)
+    cases = {int(g): body for g, body in re.findall(r"/\*BEGIN_CASE_T (\d+)\*/(.*?)/\*END_CASE_T\*/", src, re.S)}
+    assert len(cases) == len(streams) == info["types"] * opts[4]
+    nacc = info["nacc"]
+    cases_src = ""
+    for g, body in cases.items():
+        decl = "\n".join(f"  double acc{i} = 0.0;" for i in range(nacc))
+        store = "\n".join(f"  accs[{i}] = acc{i};" for i in range(nacc))
+        cases_src += CASE_T % dict(g=g, decl=decl, body=body, store=store)
+    cpp = tmp_path / "harness.cpp"
+    cpp.write_text(HARNESS % dict(body_a=body_a, cases_t=cases_src))
+    so = tmp_path / "harness.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), str(cpp)], check=True)
+    lib = C.CDLL(str(so))
+    # one random row of basis values B[dim][level] (level 0 unused) and its Phi row by the definition
+    L = int(terms.max()) + 1
+    B = rng.uniform(0.5, 1.5, size=(d, L))
+    phi = np.array([np.prod([B[l, terms[k, l]] for l in range(d) if terms[k, l] > 0]) for k in range(K)])
+    a = rng.normal(size=K)
+    # --- Phi a
+    tile = np.zeros((len(lay_a) + 1) * TRA)
+    for pos, dim, lev in lay_a:
+        tile[pos * TRA] = B[dim, lev]
+    coef = np.array([a[t] if t >= 0 else 0.0 for _, t in sorted(slot_a)])
+    out = np.zeros(1)
+    lib.run_a(tile.ctypes.data_as(C.c_void_p), coef.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert abs(out[0] - phi @ a) <= 1e-12 * np.abs(phi * a).sum()
+    # --- Phi^T: every stream's accumulators against b * Phi[k]
+    bval = 0.37
+    seen = []
+    for g, (t, tlist) in streams.items():
+        cols = [(pos, dim, lev) for (tt, pos, dim, lev) in lay_t if tt == t]
+        tile = np.zeros((len(cols) + 2) * TRT)
+        for pos, dim, lev in cols:
+            tile[pos * TRT] = B[dim, lev]
+        accs = np.zeros(nacc)
+        getattr(lib, f"run_t_{g}")(tile.ctypes.data_as(C.c_void_p), C.c_double(bval), accs.ctypes.data_as(C.c_void_p))
+        for i, k in enumerate(tlist):
+            assert abs(accs[i] - bval * phi[k]) <= 1e-13 * abs(bval * phi[k]), (g, i, k)
+        seen += tlist
+    assert sorted(seen) == list(range(K))  # every term is owned by exactly one stream
