@@ -1,0 +1,101 @@
+"""R-level drivers re-hosted in Python (outerbase_b200/fitting.py): BFGS_std / BFGS_lpdf / .lpdfwrapper of
+R/outersupport.R:30-226 and the stage-2 loop of obfit (R/fitting.R:100-136).  CPU tests run the driver over
+the oracle library; the GPU test runs the SAME driver over both libraries and compares the fits."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import borehole8d, make_problem, relerr
+from outerbase_b200 import fitting
+
+
+def test_bfgs_std_minimises_smooth_functions():
+    A = np.array([[3.0, 0.5, 0.0], [0.5, 2.0, 0.3], [0.0, 0.3, 1.0]])
+    b = np.array([1.0, -2.0, 0.5])
+
+    S = 1e4  # the stopping rule is on the scale of a log-likelihood: expected decrease < n/4, twice (R/outersupport.R:129-133)
+
+    def quad(parlist):
+        v = np.concatenate([parlist["u"], parlist["v"]])
+        return dict(val=float(S * (0.5 * v @ A @ v - b @ v)), gval=dict(u=S * (A @ v - b)[:2], v=S * (A @ v - b)[2:]))
+
+    res = fitting.BFGS_std(quad, dict(u=np.array([4.0, -3.0]), v=np.array([2.0])))
+    sol = np.linalg.solve(A, b)
+    got = np.concatenate([res["parlist"]["u"], res["parlist"]["v"]])
+    fstar = quad(dict(u=sol[:2], v=sol[2:]))["val"]
+    assert res["optid"]["val"] - fstar < 3.0  # a few times n/4
+    assert np.abs(got - sol).max() < 0.05
+
+    def walled(parlist):  # infinite outside a box, like hyplpdf (covfuncs.cpp:39-43): the line search must back off
+        x = parlist["x"]
+        if np.any(np.abs(x) > 3):
+            return dict(val=math.inf, gval=None)
+        return dict(val=float(np.sum((x - 2.5) ** 2)), gval=dict(x=2 * (x - 2.5)))
+
+    res = fitting.BFGS_std(walled, dict(x=np.array([-2.0, 0.0])), lr=1.0)
+    assert np.all(np.abs(res["parlist"]["x"]) <= 3) and res["optid"]["val"] < 1.0
+
+
+def test_knots_and_steps_helpers():
+    rng = np.random.default_rng(3)
+    x = rng.uniform(size=(500, 2))
+    kl = fitting.genknotlist([40, 16], x)
+    assert len(kl) == 2 and kl[0].size == 40 and kl[1].size == 16
+    assert np.all(np.diff(kl[0]) > 0) and 0 < kl[0][0] < kl[0][-1] < 1
+    q = np.linspace(0, 1, 40) * 40 / 41 + 0.5 / 41
+    np.testing.assert_allclose(kl[0], np.quantile(x[:, 0], q))
+    assert fitting.getsteps(100, 10000) == math.ceil(2 * 0.5 * math.sqrt((1.1 / 0.9) ** 2) * math.log(2 * 10000 * 1e-3 / 0.001))
+
+
+def _small_fit(lib, N=400, K=30):
+    om, x, y, terms, rng = make_problem(lib, N, K, covs=["mat25"] * 8, knots=[np.arange(0.001, 0.999, 0.05)] * 8)
+    logpdf = lib.lpdfvec(lib.logpr_gauss(om, terms), lib.loglik_gauss(om, terms, y, x))
+    logpdf.domarg = True
+    return om, logpdf, x, y, terms
+
+
+def test_bfgs_lpdf_on_the_oracle_improves_the_posterior(oracle):
+    om, logpdf, *_ = _small_fit(oracle)
+    par0 = dict(hyp=fitting.gethyp(om), para=fitting.getpara(logpdf))
+    start = fitting.lpdfwrapper(par0, om, logpdf)
+    res = fitting.BFGS_lpdf(om, logpdf)
+    assert math.isfinite(res["optid"]["val"]) and res["optid"]["val"] < start["val"] - 1.0
+    # om and logpdf are left at the optimum (R/outersupport.R:187-188)
+    np.testing.assert_array_equal(fitting.gethyp(om), res["parlist"]["hyp"])
+    np.testing.assert_array_equal(fitting.getpara(logpdf), res["parlist"]["para"])
+    # the reported gradient is the gradient of the reported value: central difference in the first hyper
+    h = 1e-5
+    p = {k: v.copy() for k, v in res["parlist"].items()}
+    p["hyp"][0] += h; up = fitting.lpdfwrapper(p, om, logpdf)["val"]
+    p["hyp"][0] -= 2 * h; dn = fitting.lpdfwrapper(p, om, logpdf)["val"]
+    p["hyp"][0] += h; at = fitting.lpdfwrapper(p, om, logpdf)
+    assert abs((up - dn) / (2 * h) - at["gval"]["hyp"][0]) < 1e-3 * max(1.0, abs(at["gval"]["hyp"][0])) + 5e-2
+
+
+@pytest.mark.gpu
+def test_bfgs_lpdf_gpu_matches_oracle(gpu, oracle):
+    """One driver, two libraries: every objective evaluation is updatehyp -> updateom (basis rebuild) -> optcg."""
+    out = {}
+    for name, lib in (("gpu", gpu), ("oracle", oracle)):
+        om, logpdf, *_ = _small_fit(lib)
+        res = fitting.BFGS_lpdf(om, logpdf)
+        out[name] = res
+    g, o = out["gpu"], out["oracle"]
+    assert abs(g["optid"]["val"] - o["optid"]["val"]) <= 1e-6 * abs(o["optid"]["val"])
+    assert relerr(g["parlist"]["hyp"], o["parlist"]["hyp"]) < 1e-4
+    assert relerr(g["parlist"]["para"], o["parlist"]["para"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_obfit_gauss_and_obpred_on_gpu(gpu):
+    """Stage-2 obfit + obpred on borehole data: predictions beat the constant predictor by a wide margin."""
+    rng = np.random.default_rng(8)
+    x = np.asfortranarray(rng.uniform(size=(3000, 8)))
+    y = borehole8d(x)
+    model = fitting.obfit_gauss(gpu, x, y, numb=120, covnames=["mat25pow"] * 8, numberopts=1)
+    xt = np.asfortranarray(rng.uniform(size=(500, 8)))
+    pred = fitting.obpred(model, xt)
+    yt = borehole8d(xt)
+    assert np.all(pred["var"] > 0)
+    assert np.mean((pred["mean"] - yt) ** 2) < 0.02 * np.var(yt)
