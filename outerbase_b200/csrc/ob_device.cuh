@@ -111,7 +111,7 @@ struct DevProgram {
   void upload(cudaStream_t s);
 };
 
-enum PhiMode : int { PHI_PLAIN = 0, PHI_UPDATE = 1, PHI_HESS = 2 };
+enum PhiMode : int { PHI_PLAIN = 0, PHI_UPDATE = 1, PHI_HESS = 2, PHI_DOT = 3 };
 
 struct PhiAArgs {
   const double* a = nullptr;       /* K coefficients (device) */
@@ -119,7 +119,10 @@ struct PhiAArgs {
   double* w = nullptr;             /* N: UPDATE: -((yhat-y)/sd)/sd ; HESS: (yhat/sd)/sd */
   const double* y = nullptr;       /* UPDATE */
   double sd = 1.0;
-  double* ssq_partial = nullptr;   /* UPDATE: one partial per CTA (device, >= grid entries) */
+  double* ssq_partial = nullptr;   /* UPDATE / DOT: one partial per CTA (device, >= grid entries) */
+  /* DOT (specialised kernel only): partial += wdot[n] * (out_n + y[n] * yh[n]); nothing is stored */
+  const double* wdot = nullptr;
+  const double* yh = nullptr;
   int mode = PHI_PLAIN;
 };
 
@@ -184,6 +187,9 @@ void launch_cov(Ctx& c, int kind, const double* hyp, const double* x1, u64 n1, c
                 double* out, double* outg /* may be null */);
 /* FP64 FMA peak of this GPU in TFLOP/s (micro-benchmark, ~50 ms) */
 double measure_fp64_peak(Ctx& c);
+/* C[:, j-1] = G[:, j] - G[:, 0] % B[:, j], j = 1..L: the factor the reference's domultgesub_ applies to
+ * T_k^(-l) (linalg.cpp:139-163) */
+void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out);
 /* elementwise helpers */
 void launch_fill(Ctx& c, double* p, u64 n, double v);
 /* outge[:,h] (N) dotted with w (N) -> out[h], deterministic two-stage */

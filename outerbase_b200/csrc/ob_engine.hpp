@@ -66,7 +66,13 @@ struct OuterBase {
     bool probed = false; /* disk cache looked up */
     double work = 0;    /* row-terms sent through the interpreter kernels */
     std::string why;
+    /* hyper-gradient dots (gradhyp_dots_spec): per-dimension column tables whose dim-l entries point
+     * into the scratch columns, and their host images */
+    std::vector<std::unique_ptr<obd::ColTable>> gtab;
+    std::vector<const double*> gsrc_host;
+    std::vector<int> gops_host;
   };
+  DevBuf<double> tmpC, tmpKd, tmpHp;
   std::list<SpecEntry> specs;
   /* terms installed by set_terms for the *_dev entry points */
   std::vector<u64> cur_terms;
@@ -246,6 +252,61 @@ struct OuterBase {
   void phi_t(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev) {
     if (SpecEntry* e = spec_for(terms, K)) { obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), w_dev, out_dev, ws); return; }
     obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
+  }
+
+  /* gradhyp[h] = sum_n w_n * outge[n,h] for every hyper-parameter, outge = prodmmge_ (linalg.cpp:225-277), in the
+   * reference's own form (domultgesub_, linalg.cpp:139-163, 273-276):
+   *   outge[:,h] = basescale % ( sum_{k: t_kl>0} a_k T_k^(-l) % (G_h[:,t_kl] - G_h[:,0] % B_l[:,t_kl]) ) + G_h[:,0] % yhat
+   * i.e. ONE plain product per hyper-parameter with the coefficients of the terms that skip dimension l zeroed and
+   * dimension l's columns replaced by C_j = G_j - G_0 % B_j.  Same terms table => the specialised Phi a kernel runs it
+   * with another column-pointer table; its PHI_DOT epilogue folds the dot with w, so yhatge is never stored.
+   * Returns false when the table is not specialised (the caller then uses the augmented interpreter programs). */
+  bool gradhyp_dots_spec(const u64* terms, u64 K, const std::vector<double>& coeff_host, const double* w_dev, const double* yhat_dev,
+                         double* out_dev /* H */) {
+    if (!dograd || H == 0) return false;
+    SpecEntry* e = spec_for(terms, K);
+    if (!e) return false;
+    const obt::Program& P = e->pa->host;
+    const size_t nc = P.cols.size();
+    std::vector<u64> lmax(d, 0);
+    for (const obt::ColRef& cr : P.cols) lmax[cr.dim] = std::max<u64>(lmax[cr.dim], cr.level);
+    u64 lall = 1;
+    for (u64 l = 0; l < d; ++l) lall = std::max(lall, lmax[l]);
+    tmpC.ensure(ld * lall);
+    /* masked coefficients, one copy per dimension */
+    std::vector<double> am(d * K);
+    for (u64 l = 0; l < d; ++l)
+      for (u64 k = 0; k < K; ++k) am[l * K + k] = terms[k + l * K] > 0 ? coeff_host[k] : 0.0;
+    tmpKd.upload(am, ctx.stream);
+    /* per-dimension column tables */
+    if (e->gtab.size() != d) { e->gtab.clear(); for (u64 l = 0; l < d; ++l) e->gtab.emplace_back(new obd::ColTable()); }
+    e->gsrc_host.assign(d * nc, nullptr);
+    e->gops_host.assign(nc, obd::COL_COPY);
+    for (u64 l = 0; l < d; ++l) {
+      for (size_t c = 0; c < nc; ++c) {
+        const obt::ColRef& cr = P.cols[c];
+        e->gsrc_host[l * nc + c] = cr.dim == l ? tmpC.p + (cr.level - 1) * ld : basemat.p + (knotptst[cr.dim] + cr.level) * ld;
+      }
+      obd::ColTable& ct = *e->gtab[l];
+      ct.ncol = ct.nload = (int)nc; ct.has_ops = false;
+      ct.load_src.upload(e->gsrc_host.data() + l * nc, nc, ctx.stream);
+      ct.col_op.upload(e->gops_host.data(), nc, ctx.stream);
+    }
+    tmpHp.ensure(H * (u64)ctx.sms);
+    for (u64 h = 0; h < H; ++h) {
+      const u64 l = hypmatch[h];
+      const double* G = basematge.p + gest[h] * ld;
+      obd::launch_gradcols(ctx, basemat.p + knotptst[l] * ld, G, ld, lmax[l], tmpC.p);
+      obd::PhiPlan pl;
+      pl.prog = e->pa.get(); pl.cols = e->gtab[l].get(); pl.scale = scale.p; pl.sq = 0; pl.N = N;
+      obd::PhiAArgs a;
+      a.a = tmpKd.p + l * K; a.mode = obd::PHI_DOT; a.y = G; a.wdot = w_dev; a.yh = yhat_dev; a.ssq_partial = tmpHp.p + h * ctx.sms;
+      int grid = 0;
+      obd::launch_phi_a_spec(ctx, *e->k, pl, a, ws, &grid);
+      obd::launch_sum_partials(ctx, tmpHp.p + h * ctx.sms, grid, out_dev + h);
+    }
+    ctx.sync(); /* the host images above must outlive the uploads */
+    return true;
   }
 
   obd::ColTable* coltable(const obd::DevProgram* prog, int sq, int h) {
@@ -615,7 +676,8 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     if (grid > 0) obd::launch_sum_partials(ctx, ob.ws.ssq.p, grid, red.p + K);
     const bool dohyp = compute_grad && compute_gradhyp;
     if (compute_grad) ob.phi_t(terms.data(), K, 0, w.p, red.p);
-    if (dohyp) { /* gradhyp = residtemp^T * yhatge, :127 -- yhatge column h is never stored */
+    if (dohyp && !ob.gradhyp_dots_spec(terms.data(), K, coeff, w.p, yhat.p, red.p + K + 1)) {
+      /* gradhyp = residtemp^T * yhatge, :127 -- yhatge column h is never stored */
       gebuf.ensure(ob.ld + 4 * ctx.sms);
       for (u64 h = 0; h < H; ++h) {
         obd::PhiAArgs g; g.a = kbuf.p; g.out = gebuf.p; g.mode = obd::PHI_PLAIN;

@@ -1061,6 +1061,19 @@ void launch_sum_partials(Ctx& c, const double* partial, int n, double* out) {
   check_launch(c, "sum_partials_kernel");
 }
 
+__global__ void gradcols_kernel(const double* __restrict__ B, const double* __restrict__ G, unsigned long long ld, unsigned long long L,
+                                double* __restrict__ out) {
+  const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= ld) return;
+  const double g0 = G[n];
+  for (unsigned long long j = 1; j <= L; ++j) out[n + (j - 1) * ld] = G[n + j * ld] - g0 * B[n + j * ld];
+}
+void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out) {
+  if (ld == 0 || L == 0) return;
+  gradcols_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, c.stream>>>(B, G, ld, L, out);
+  check_launch(c, "gradcols_kernel");
+}
+
 void launch_fill(Ctx& c, double* p, u64 n, double v) {
   if (n == 0) return;
   fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(p, n, v);

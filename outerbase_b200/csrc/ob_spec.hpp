@@ -38,6 +38,7 @@ struct SpecParams {
   double* ssq_partial;
   double* partial;
   const double* a;
+  const double* yh;
   const int* slot_term;
   double sd;
   unsigned long long N;
@@ -57,6 +58,8 @@ struct SpecOptions {
   /* Phi^T: 1 = form a cluster of the CTA types and multicast the tile (when 2 <= types <= 8, np >= 2).
    * Correct but measured 2-3x slower than L2-served repeats on B200 (profiles/r01_spec_sweeps.txt): off. */
   int mc = 0;
+  /* Phi^T: passes of a tile interleaved by the compiler (unroll factor of the pass loop) */
+  int ut = 1;
 };
 
 struct SpecSource {
@@ -327,7 +330,7 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
     size_t maxcols = 1;
     for (auto& tc : tcols) maxcols = std::max(maxcols, tc.size());
     if (S.cluster > 1) maxcols = P.cols.size(); /* multicast: every CTA receives every column */
-    hdr.f("#define OBS_CL %d\n", S.cluster);
+    hdr.f("#define OBS_CL %d\n#define OBS_UT %d\n", S.cluster, std::max(1, opt.ut));
     tab.f("__device__ const unsigned short obs_cols_all[] = {");
     for (size_t c = 0; c < P.cols.size(); ++c) tab.f("%d,", (int)c);
     tab.f("0};\n");

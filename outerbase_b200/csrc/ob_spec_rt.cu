@@ -140,10 +140,10 @@ struct SpecKernels {
 
 obs::SpecOptions spec_default_options() {
   obs::SpecOptions o;
-  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc -- tuning only */
-    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc};
+  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut -- tuning only */
+    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut};
     int i = 0;
-    for (const char* p = e; *p && i < 11; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (const char* p = e; *p && i < 12; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
   }
   return o;
 }
@@ -242,7 +242,8 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
   p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles;
   p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
   const int grid = std::max(1, std::min(p.ntiles, c.sms));
-  if (a.mode == PHI_UPDATE) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
+  if (a.mode == PHI_UPDATE || a.mode == PHI_DOT) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
+  if (a.mode == PHI_DOT) { p.win = a.wdot; p.yh = a.yh; }
   p.a = a.a; p.slot_term = pl.prog->slot_term.p; p.nslots = (int)pl.prog->host.nslots();
   spec_launch(c, k.ka, k.smem_a_set, grid, 32 * (warps + k.opt.np), g.smem, p, "phi_a_spec");
   if (grid_out) *grid_out = grid;

@@ -91,11 +91,14 @@ def test_spec_loglik_and_optcg(spec, oracle):
     coeff = rng.normal(size=K) / 100
     g = rng.normal(size=K)
     for T in (O, G):
+        T[6].compute_gradhyp = True; T[6].compute_gradpara = True
         T[6].updatepara([np.log(0.1)])
         T[6].update(coeff)
     lo, lg = O[6], G[6]
     assert abs(lg.val - lo.val) <= 1e-8 * abs(lo.val)
     assert relerr(lg.grad, lo.grad) < 1e-8
+    assert relerr(lg.gradhyp, lo.gradhyp) < 1e-7  # reference-form hyper-gradient on the specialised kernel (PHI_DOT)
+    assert relerr(lg.gradpara, lo.gradpara) < 1e-8
     assert relerr(lg.yhat, lo.yhat) < 1e-9
     assert relerr(lg.hessmult(g), lo.hessmult(g)) < 1e-8
     assert relerr(lg.diaghess(), lo.diaghess()) < 1e-8
@@ -106,6 +109,7 @@ def test_spec_loglik_and_optcg(spec, oracle):
     assert vg.cg_iters == vo.cg_iters
     assert abs(vg.val - vo.val) <= 1e-8 * abs(vo.val)
     assert relerr(vg.coeff, vo.coeff) < 1e-8
+    assert relerr(vg.gradhyp, vo.gradhyp) < 1e-6
 
 
 def test_spec_full_size_properties(spec):

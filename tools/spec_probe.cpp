@@ -20,8 +20,8 @@ int main(int argc, char** argv) {
   std::vector<uint64_t> terms(K * d);
   in.read((char*)terms.data(), K * d * 8);
   obs::SpecOptions o;
-  int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc};
-  for (int i = 0; i < 11 && 3 + i < argc; ++i) *f[i] = std::atoi(argv[3 + i]);
+  int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut};
+  for (int i = 0; i < 12 && 3 + i < argc; ++i) *f[i] = std::atoi(argv[3 + i]);
   auto t0 = std::chrono::steady_clock::now();
   const int types = obs::choose_types(terms.data(), K, d, o);
   if (!types) { std::fprintf(stderr, "terms table is not trie-compilable\n"); return 1; }
