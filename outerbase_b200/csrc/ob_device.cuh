@@ -188,8 +188,13 @@ void launch_cov(Ctx& c, int kind, const double* hyp, const double* x1, u64 n1, c
 /* FP64 FMA peak of this GPU in TFLOP/s (micro-benchmark, ~50 ms) */
 double measure_fp64_peak(Ctx& c);
 /* C[:, j-1] = G[:, j] - G[:, 0] % B[:, j], j = 1..L: the factor the reference's domultgesub_ applies to
- * T_k^(-l) (linalg.cpp:139-163) */
-void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out);
+ * T_k^(-l) (linalg.cpp:139-163); sq: the same for the squared matrices, basematsq_gradhyp = 2 G % B
+ * (modandbase.cpp:588-590): C_j = 2 B_j % (G_j - G_0 % B_j) */
+void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out, int sq = 0);
+/* out[n] = c * g[n] * w[n] */
+void launch_scaled_product(Ctx& c, double coef, const double* g, const double* w, u64 n, double* out);
+/* out[k] = a[k] + (mask[k] ? b[k] : 0) */
+void launch_masked_add(Ctx& c, const double* a, const double* b, const unsigned char* mask, u64 n, double* out);
 /* elementwise helpers */
 void launch_fill(Ctx& c, double* p, u64 n, double v);
 /* outge[:,h] (N) dotted with w (N) -> out[h], deterministic two-stage */

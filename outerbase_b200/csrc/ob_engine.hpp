@@ -68,11 +68,12 @@ struct OuterBase {
     std::string why;
     /* hyper-gradient dots (gradhyp_dots_spec): per-dimension column tables whose dim-l entries point
      * into the scratch columns, and their host images */
-    std::vector<std::unique_ptr<obd::ColTable>> gtab;
-    std::vector<const double*> gsrc_host;
-    std::vector<int> gops_host;
+    std::vector<std::unique_ptr<obd::ColTable>> gtab, gtab_t;
+    std::vector<const double*> gsrc_host, gsrc_t_host;
+    std::vector<int> gops_host, gops_t_host;
   };
-  DevBuf<double> tmpC, tmpKd, tmpHp;
+  DevBuf<double> tmpC, tmpKd, tmpHp, tmpNg, tmpK2;
+  DevBuf<unsigned char> tmpMask;
   std::list<SpecEntry> specs;
   /* terms installed by set_terms for the *_dev entry points */
   std::vector<u64> cur_terms;
@@ -366,11 +367,62 @@ struct OuterBase {
       obd::launch_phi_a(ctx, plan(program(terms, K, (int)hypmatch[h]), sq, (int)h), a, ws, nullptr);
     }
   }
+  /* tprodmmge_'s outge (linalg.cpp:394-471) in the reference's own form (dotmultgesub_, :364-386) on the specialised
+   * Phi^T kernel: column h = Phi^T (G_h[:,0] % w) + [t_kl > 0] % Phi_C^T w, where Phi_C is the plain product with
+   * dimension l's columns replaced by C_j = G_j - G_0 % B_j (squared operators: 2 G_0, C_j = 2 B_j (G_j - G_0 B_j),
+   * every other column squared in shared memory).  Two plain products per hyper-parameter on the same terms table. */
+  bool tmm_ge_spec(const u64* terms, u64 K, int sq, const double* w_dev, double* outge_dev /* K x H, local sums */) {
+    if (!dograd || H == 0) return false;
+    SpecEntry* e = spec_for(terms, K);
+    if (!e) return false;
+    const obt::Program& P = e->pt->host;
+    const size_t nc = P.cols.size();
+    std::vector<u64> lmax(d, 0);
+    for (const obt::ColRef& cr : P.cols) lmax[cr.dim] = std::max<u64>(lmax[cr.dim], cr.level);
+    u64 lall = 1;
+    for (u64 l = 0; l < d; ++l) lall = std::max(lall, lmax[l]);
+    tmpC.ensure(ld * lall);
+    tmpNg.ensure(ld);
+    tmpK2.ensure(2 * K);
+    std::vector<unsigned char> mask(d * K);
+    for (u64 l = 0; l < d; ++l)
+      for (u64 k = 0; k < K; ++k) mask[l * K + k] = terms[k + l * K] > 0 ? 1 : 0;
+    tmpMask.upload(mask, ctx.stream);
+    if (e->gtab_t.size() != d) { e->gtab_t.clear(); for (u64 l = 0; l < d; ++l) e->gtab_t.emplace_back(new obd::ColTable()); }
+    e->gsrc_t_host.assign(d * nc, nullptr);
+    e->gops_t_host.assign(d * nc, obd::COL_COPY);
+    for (u64 l = 0; l < d; ++l) {
+      for (size_t c = 0; c < nc; ++c) {
+        const obt::ColRef& cr = P.cols[c];
+        const bool mine = cr.dim == l;
+        e->gsrc_t_host[l * nc + c] = mine ? tmpC.p + (cr.level - 1) * ld : basemat.p + (knotptst[cr.dim] + cr.level) * ld;
+        e->gops_t_host[l * nc + c] = (sq && !mine) ? obd::COL_SQUARE : obd::COL_COPY;
+      }
+      obd::ColTable& ct = *e->gtab_t[l];
+      ct.ncol = ct.nload = (int)nc; ct.has_ops = sq != 0;
+      ct.load_src.upload(e->gsrc_t_host.data() + l * nc, nc, ctx.stream);
+      ct.col_op.upload(e->gops_t_host.data() + l * nc, nc, ctx.stream);
+    }
+    for (u64 h = 0; h < H; ++h) {
+      const u64 l = hypmatch[h];
+      const double* G = basematge.p + gest[h] * ld;
+      obd::launch_scaled_product(ctx, sq ? 2.0 : 1.0, G, w_dev, N, tmpNg.p); /* rows beyond N are masked by the kernel */
+      obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), tmpNg.p, tmpK2.p, ws);
+      obd::launch_gradcols(ctx, basemat.p + knotptst[l] * ld, G, ld, lmax[l], tmpC.p, sq);
+      obd::PhiPlan pl;
+      pl.prog = e->pt.get(); pl.cols = e->gtab_t[l].get(); pl.scale = scale.p; pl.sq = sq; pl.N = N;
+      obd::launch_phi_t_spec(ctx, *e->k, pl, w_dev, tmpK2.p + K, ws);
+      obd::launch_masked_add(ctx, tmpK2.p, tmpK2.p + K, tmpMask.p + l * K, K, outge_dev + h * K);
+    }
+    ctx.sync(); /* the host images above must outlive the uploads */
+    return true;
+  }
   void tmm_ge_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev /* K*(1+H): out | outge */) {
     if (!dograd) throw std::logic_error("outerbase was built without gradients");
     phi_t(terms, K, sq, w_dev, out_dev);
-    for (u64 h = 0; h < H; ++h)
-      obd::launch_phi_t(ctx, plan(program(terms, K, (int)hypmatch[h], 1), sq, (int)h), w_dev, out_dev + (1 + h) * K, ws);
+    if (!tmm_ge_spec(terms, K, sq, w_dev, out_dev + K))
+      for (u64 h = 0; h < H; ++h)
+        obd::launch_phi_t(ctx, plan(program(terms, K, (int)hypmatch[h], 1), sq, (int)h), w_dev, out_dev + (1 + h) * K, ws);
     ctx.allreduce_sum(out_dev, K * (1 + H));
   }
 

@@ -1062,16 +1062,40 @@ void launch_sum_partials(Ctx& c, const double* partial, int n, double* out) {
 }
 
 __global__ void gradcols_kernel(const double* __restrict__ B, const double* __restrict__ G, unsigned long long ld, unsigned long long L,
-                                double* __restrict__ out) {
+                                double* __restrict__ out, int sq) {
   const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= ld) return;
   const double g0 = G[n];
-  for (unsigned long long j = 1; j <= L; ++j) out[n + (j - 1) * ld] = G[n + j * ld] - g0 * B[n + j * ld];
+  for (unsigned long long j = 1; j <= L; ++j) {
+    const double b = B[n + j * ld];
+    const double c = G[n + j * ld] - g0 * b;
+    out[n + (j - 1) * ld] = sq ? 2.0 * (b * c) : c;
+  }
 }
-void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out) {
+void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out, int sq) {
   if (ld == 0 || L == 0) return;
-  gradcols_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, c.stream>>>(B, G, ld, L, out);
+  gradcols_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, c.stream>>>(B, G, ld, L, out, sq);
   check_launch(c, "gradcols_kernel");
+}
+__global__ void scaled_product_kernel(double coef, const double* __restrict__ g, const double* __restrict__ w, unsigned long long n,
+                                      double* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = coef * (g[i] * w[i]);
+}
+void launch_scaled_product(Ctx& c, double coef, const double* g, const double* w, u64 n, double* out) {
+  if (n == 0) return;
+  scaled_product_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(coef, g, w, n, out);
+  check_launch(c, "scaled_product_kernel");
+}
+__global__ void masked_add_kernel(const double* __restrict__ a, const double* __restrict__ b, const unsigned char* __restrict__ mask,
+                                  unsigned long long n, double* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mask[i] ? a[i] + b[i] : a[i];
+}
+void launch_masked_add(Ctx& c, const double* a, const double* b, const unsigned char* mask, u64 n, double* out) {
+  if (n == 0) return;
+  masked_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a, b, mask, n, out);
+  check_launch(c, "masked_add_kernel");
 }
 
 void launch_fill(Ctx& c, double* p, u64 n, double v) {

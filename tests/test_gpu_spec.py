@@ -69,6 +69,25 @@ def test_spec_agrees_with_interpreter_and_state(gpu, oracle):
     np.testing.assert_array_equal(t1, ob.tmatmul(terms, r))  # run-to-run bit reproducible
 
 
+def test_auto_policy_switches_after_the_table_proved_hot(gpu):
+    """spec = 2 (default): interpreter kernels until `spec_work` row-terms went through them, then the compiled module."""
+    om, x, y, terms, rng = make_problem(gpu, 4000, 200)
+    ob = gpu.outerbase(om, x)
+    a = rng.normal(size=200)
+    gpu.set_option("spec", 2)
+    gpu.set_option("spec_work", 3.5 * 4000 * 200)  # three products stay interpreted, the fourth compiles
+    try:
+        y0 = ob.matmul(terms, a)
+        assert ob.spec_state(terms) == 0
+        ob.matmul(terms, a); ob.matmul(terms, a)
+        assert ob.spec_state(terms) == 0
+        y1 = ob.matmul(terms, a)
+        assert ob.spec_state(terms) == 1
+    finally:
+        gpu.set_option("spec_work", 4e12)
+    assert relerr(y1, y0) < 1e-13
+
+
 def test_spec_squared_operators(spec, oracle):
     o = oracle_basis(oracle, 1000, 200)
     omg, x, y, terms, rng = make_problem(spec, 1000, 200)
@@ -79,6 +98,10 @@ def test_spec_squared_operators(spec, oracle):
     assert relerr(obg.sqtmm(terms, r), ob.sqtmm(terms, r)) < 1e-9
     assert relerr(obg.sqcolsums(terms), ob.sqcolsums(terms)) < 1e-9
     assert obg.spec_state(terms) == 1
+    # hyper-gradient operators in the reference's form on the specialised Phi^T kernel (tmm_ge_spec)
+    assert relerr(obg.tmatmul_gradhyp(terms, r), ob.tmatmul_gradhyp(terms, r)) < 1e-8
+    assert relerr(obg.sqtmm_gradhyp(terms, r), ob.sqtmm_gradhyp(terms, r)) < 1e-8
+    assert relerr(obg.sqcolsums_gradhyp(terms), ob.sqcolsums_gradhyp(terms)) < 1e-8
 
 
 def test_spec_loglik_and_optcg(spec, oracle):
