@@ -217,7 +217,7 @@ int ob_outerbase_mm_dev(ob_outerbase* ob, int sq, const double* a_dev, double* o
   OB_TRY obe::OuterBase& b = *ob->ob; b.mm_dev(b.cur_terms.data(), b.cur_K, sq, a_dev, out_dev); OB_CATCH
 }
 int ob_outerbase_tmm_dev(ob_outerbase* ob, int sq, const double* a_dev, double* out_dev) {
-  OB_TRY obe::OuterBase& b = *ob->ob; b.tmm_dev(b.cur_terms.data(), b.cur_K, sq, a_dev, out_dev); OB_CATCH
+  OB_TRY obe::OuterBase& b = *ob->ob; b.tmm_dev(b.cur_terms.data(), b.cur_K, sq, a_dev, out_dev, true, b.N); OB_CATCH
 }
 int ob_outerbase_mm_mat_dev(ob_outerbase* ob, int sq, const double* A_dev, uint64_t C, double* out_dev) {
   OB_TRY obe::OuterBase& b = *ob->ob; b.mm_mat_dev(b.cur_terms.data(), b.cur_K, sq, A_dev, C, out_dev, b.N); OB_CATCH

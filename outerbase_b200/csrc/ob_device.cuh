@@ -162,6 +162,9 @@ std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const ob
 double spec_compile_seconds(const SpecKernels& k);
 std::string spec_compile_nocache(const std::string& src, double* seconds);
 bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol);
+bool spec_uses_cluster(const SpecKernels& k);
+/* true when [p, p + bytes) lies inside one device allocation (cuMemGetAddressRange through the runtime's driver entry point) */
+bool device_range_readable(const void* p, size_t bytes);
 void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
 void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
 /* explicit Phi (N x K column-major, device), getm_ linalg.cpp:685-715 */

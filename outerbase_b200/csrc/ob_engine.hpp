@@ -250,8 +250,22 @@ struct OuterBase {
     if (SpecEntry* e = spec_for(terms, K)) { obd::launch_phi_a_spec(ctx, *e->k, plan(e->pa.get(), sq, -1), a, ws, grid_out); return; }
     obd::launch_phi_a(ctx, plan(program(terms, K, -1), sq, -1), a, ws, grid_out);
   }
-  void phi_t(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev) {
-    if (SpecEntry* e = spec_for(terms, K)) { obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), w_dev, out_dev, ws); return; }
+  /* The specialised kernel stages the input vector with bulk copies of whole 128-row tiles, so it reads up to the
+   * padded row count `ld` of a 16-byte aligned source.  Library buffers are padded; a caller's device buffer
+   * (w_rows < ld) is used in place when the device allocation it lives in extends that far (the driver tells), and
+   * copied to a padded buffer otherwise. */
+  DevBuf<double> tmpW;
+  void phi_t(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, u64 w_rows = ~(u64)0) {
+    if (SpecEntry* e = spec_for(terms, K)) {
+      const bool misaligned = reinterpret_cast<uintptr_t>(w_dev) & 15u;
+      if (misaligned || (w_rows < ld && N % 256 != 0 && !obd::device_range_readable(w_dev, ld * sizeof(double)))) {
+        tmpW.ensure(ld);
+        OB_CUDA(cudaMemcpyAsync(tmpW.p, w_dev, N * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+        w_dev = tmpW.p;
+      }
+      obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), w_dev, out_dev, ws);
+      return;
+    }
     obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
   }
 
@@ -354,8 +368,8 @@ struct OuterBase {
     obd::PhiAArgs a; a.a = a_dev; a.out = out_dev; a.mode = obd::PHI_PLAIN;
     phi_a(terms, K, sq, a, nullptr);
   }
-  void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true) {
-    phi_t(terms, K, sq, w_dev, out_dev);
+  void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true, u64 w_rows = ~(u64)0) {
+    phi_t(terms, K, sq, w_dev, out_dev, w_rows);
     if (reduce_ranks) ctx.allreduce_sum(out_dev, K);
   }
   /* prodmmge_: outge column h = augmented-program product (ob_terms.hpp) */
@@ -467,7 +481,7 @@ struct OuterBase {
     for (u64 c = 0; c < C; ++c) mm_dev(terms, K, sq, A_dev + c * K, out_dev + c * ldo);
   }
   void tmm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 lda, u64 C, double* out_dev) {
-    for (u64 c = 0; c < C; ++c) tmm_dev(terms, K, sq, A_dev + c * lda, out_dev + c * K, false);
+    for (u64 c = 0; c < C; ++c) tmm_dev(terms, K, sq, A_dev + c * lda, out_dev + c * K, false, c + 1 < C ? ld : lda);
     ctx.allreduce_sum(out_dev, K * C);
   }
   void mm_mat(int sq, const u64* terms, u64 K, const double* A, u64 C, double* out) {

@@ -164,6 +164,26 @@ std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const ob
   return k;
 }
 
+bool spec_uses_cluster(const SpecKernels& k) { return k.cluster > 1; }
+
+bool device_range_readable(const void* p, size_t bytes) {
+  using Fn = int (*)(unsigned long long*, size_t*, unsigned long long);
+  static Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<Fn>(f);
+  }
+  if (!fn) return false;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return false;
+  const unsigned long long lo = (unsigned long long)(uintptr_t)p;
+  return lo >= base && lo + bytes <= base + size;
+}
 double spec_compile_seconds(const SpecKernels& k) { return k.from_cache ? 0.0 : k.compile_seconds; }
 
 static void spec_fill(obs::SpecParams& p, const PhiPlan& pl, int TR) {
