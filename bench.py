@@ -346,7 +346,7 @@ def main():
         # `ncu --set full` capture of this exact workload (profiles/r01_spec_ncu_summary.md); other shapes: null
         traffic, traffic_src = None, None
         if args.spec == "1" and world == 1 and N == N_TOTAL:
-            traffic = {"phi_t_spec": 616.340e6 + 3.624e6, "phi_a_spec": 608.137e6 + 10.519e6}[dom]
+            traffic = {"phi_t_spec": 616.647e6 + 10.765e6, "phi_a_spec": 608.288e6 + 10.569e6}[dom]
             traffic_src = "ncu --set full, profiles/r01_spec_ncu_summary.md (bytes per launch)"
         roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
