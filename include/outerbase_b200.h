@@ -142,6 +142,10 @@ int ob_outerbase_mm_mat(ob_outerbase* ob, int sq, const uint64_t* terms, uint64_
                         const double* A /* K x C */, uint64_t C, double* out /* N x C */);
 int ob_outerbase_tmm_mat(ob_outerbase* ob, int sq, const uint64_t* terms, uint64_t K,
                          const double* A /* N x C */, uint64_t C, double* out /* K x C */);
+/* outerbase::residvar / residvar_gradhyp (src/modandbase.cpp:889-922): variance of the terms left out of
+ * the basis, 1 - sqmm(terms, getvar(terms)), and its hyper-gradient (N x H). */
+int ob_outerbase_residvar(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out /* N */);
+int ob_outerbase_residvar_gradhyp(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out /* N x H */);
 /* Device-pointer forms of mm / tmm / mm_mat for callers that keep vectors in HBM
  * (the CG loop, bench.py's `value`).  All *_dev pointers are device memory on
  * ctx's GPU; work is enqueued on ctx's stream and NOT synchronised. */
@@ -232,6 +236,10 @@ int ob_getm(ob_ctx* ctx, double* out, const uint64_t* terms, uint64_t K, uint64_
 int ob_loglik_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K,
                            const double* y, const double* x, uint64_t N, ob_lpdf** out);
 int ob_logpr_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K, ob_lpdf** out);
+/* new(loglik_gda, om, terms, y, x) -- src/lpdfs/loglik_gda.cpp:47-239, src/interfaceR.cpp:745-750: the stage-1
+ * likelihood of obfit (R/fitting.R:84), two parameters (noisescale, lik.coeffscale); flag "dodiag" = doda. */
+int ob_loglik_gda_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K,
+                         const double* y, const double* x, uint64_t N, ob_lpdf** out);
 /* new(lpdfvec, a, b): a is child 0 (grad/gradhyp are sized from it, fit.cpp:338-343). */
 int ob_lpdfvec_create(ob_lpdf* a, ob_lpdf* b, ob_lpdf** out);
 int ob_lpdf_destroy(ob_lpdf* l);

@@ -1073,6 +1073,23 @@ mat outerbase::sqtmm_gradhyp(const umat& terms, const vec& a) const {
   return g;
 }
 vec outerbase::sqcolsums(const umat& terms) const { vec ro(n_row, 1.0); return sqtmm(terms, ro); }
+vec outerbase::residvar(const umat& terms) const { /* :889-896, assumes a correlation function */
+  vec out = sqmm(terms, om.getvar(terms));
+  for (double& v : out) v = 1 - v;
+  return out;
+}
+mat outerbase::residvar_gradhyp(const umat& terms) const { /* :904-922 */
+  const vec varc = om.getvar(terms);
+  mat outge = sqmm_gradhyp(terms, varc);
+  for (double& v : outge.a) v = -v;
+  mat l2 = om.getlvar_gradhyp(terms);
+  for (u64 h = 0; h < l2.nc; ++h)
+    for (u64 k = 0; k < l2.nr; ++k) l2(k, h) *= varc[k];
+  mat l3;
+  prodmm_mat_(l3, terms, l2, basematsq, basescalesq, knotptst, lv());
+  for (u64 i = 0; i < outge.a.size(); ++i) outge.a[i] -= l3.a[i];
+  return outge;
+}
 mat outerbase::sqcolsums_gradhyp(const umat& terms) const { vec ro(n_row, 1.0); return sqtmm_gradhyp(terms, ro); }
 
 /* ------------------------------------------------------------------ lpdf */
@@ -1268,6 +1285,134 @@ mat loglik_gauss::diaghessgradpara() { /* :176-179 */
   const double c = -2 * std::exp(-2 * para[0]);
   for (u64 i = 0; i < lh.size(); ++i) o(i, 0) = c * lh[i];
   return o;
+}
+
+/* ---- loglik_gda ---- */
+loglik_gda::loglik_gda(const outermod& om_, const umat& terms_, const vec& y_, const mat& x_)
+    : om(om_), ob(om_, x_, true), y(y_), x(x_) { /* :47-68 */
+  terms = terms_;
+  npara = 2;
+  para0 = {0.5 * std::log(0.01 * arma_var(y.data(), y.size())), 0.0};
+  paravar = {4, 4};
+  para = para0;
+  buildstd();
+  nterms = terms.nr;
+}
+void loglik_gda::setnthreads(int k) { ob.nthreads = k; }                                /* :75-77 */
+void loglik_gda::updateom() { ob.build(); if (doda) redostd = true; }                    /* :84-87 */
+void loglik_gda::updatepara(const vec& p) { para = p; redostd = true; }                   /* :94-97 */
+void loglik_gda::updateterms(const umat& t) { terms = t; nterms = terms.nr; if (doda) redostd = true; } /* :104-108 */
+void loglik_gda::buildstd() { /* :217-236 */
+  if (redostd) {
+    const u64 N = y.size();
+    vec obsvar(N, std::exp(2 * para[0]));
+    const vec rterms = ob.residvar(terms);
+    if (doda) for (u64 i = 0; i < N; ++i) obsvar[i] += std::exp(2 * para[1]) * rterms[i];
+    obssd.resize(N);
+    for (u64 i = 0; i < N; ++i) obssd[i] = std::sqrt(obsvar[i]);
+    if (doda) {
+      obssd_gradhyp = ob.residvar_gradhyp(terms);
+      for (u64 h = 0; h < obssd_gradhyp.nc; ++h)
+        for (u64 i = 0; i < N; ++i) obssd_gradhyp(i, h) *= (std::exp(2 * para[1]) * 0.5) / obssd[i];
+    }
+    obssd_gradpara = mat(N, 2);
+    for (u64 i = 0; i < N; ++i) {
+      obssd_gradpara(i, 0) = std::exp(2 * para[0]) / obssd[i];
+      obssd_gradpara(i, 1) = doda ? std::exp(2 * para[1]) * rterms[i] / obssd[i] : 0.0;
+    }
+  }
+  redostd = false;
+}
+void loglik_gda::update(const vec& coeff_) { /* :116-149 */
+  coeff = coeff_;
+  const u64 N = y.size();
+  if (compute_gradhyp) ob.mm_gradhyp(yhat, yhatge, terms, coeff);
+  else ob.mm(yhat, terms, coeff);
+  buildstd();
+  residtemp.resize(N); residtemp2.resize(N);
+  for (u64 i = 0; i < N; ++i) { residtemp[i] = (yhat[i] - y[i]) / obssd[i]; residtemp2[i] = residtemp[i] * residtemp[i]; }
+  if (compute_val) {
+    vec t(N);
+    for (u64 i = 0; i < N; ++i) t[i] = std::log(obssd[i]);
+    val = -0.5 * accu2(residtemp2.data(), N) - accu2(t.data(), N);
+  }
+  if (compute_grad) {
+    vec inv(N);
+    for (u64 i = 0; i < N; ++i) { residtemp[i] = -1. * (residtemp[i] / obssd[i]); residtemp2[i] /= obssd[i]; inv[i] = 1 / obssd[i]; }
+    ob.tmm(grad, terms, residtemp);
+    if (compute_gradhyp) {
+      gradhyp.assign(ob.n_hyp, 0.0);
+      for (u64 h = 0; h < ob.n_hyp; ++h) {
+        gradhyp[h] = dot2(residtemp.data(), yhatge.col(h), N);
+        if (doda) {
+          gradhyp[h] += dot2(residtemp2.data(), obssd_gradhyp.col(h), N);
+          gradhyp[h] -= dot2(inv.data(), obssd_gradhyp.col(h), N);
+        }
+      }
+    }
+    if (compute_gradpara) {
+      gradpara.assign(2, 0.0);
+      for (u64 c = 0; c < 2; ++c) {
+        gradpara[c] = dot2(residtemp2.data(), obssd_gradpara.col(c), N);
+        gradpara[c] -= dot2(inv.data(), obssd_gradpara.col(c), N);
+      }
+    }
+  }
+}
+vec loglik_gda::hessmult(const vec& g) { /* :156-164 */
+  ob.mm(yhattemp, terms, g);
+  for (u64 i = 0; i < yhattemp.size(); ++i) { yhattemp[i] /= obssd[i]; yhattemp[i] /= obssd[i]; }
+  ob.tmm(gradtemp, terms, yhattemp);
+  return gradtemp;
+}
+vec loglik_gda::diaghess() { /* :172-175 */
+  vec t(obssd.size());
+  for (u64 i = 0; i < t.size(); ++i) t[i] = 1 / (obssd[i] * obssd[i]);
+  return ob.sqtmm(terms, t);
+}
+mat loglik_gda::diaghessgradhyp() { /* :182-196 */
+  const u64 N = obssd.size();
+  vec temp(N);
+  for (u64 i = 0; i < N; ++i) temp[i] = 1 / (obssd[i] * obssd[i]);
+  mat lh = ob.sqtmm_gradhyp(terms, temp);
+  for (u64 i = 0; i < N; ++i) temp[i] *= -2 / obssd[i];
+  if (doda) {
+    mat t2 = obssd_gradhyp;
+    for (u64 h = 0; h < t2.nc; ++h)
+      for (u64 i = 0; i < N; ++i) t2(i, h) *= temp[i];
+    const mat add = ob.sqtmmm(terms, t2);
+    for (u64 i = 0; i < lh.a.size(); ++i) lh.a[i] += add.a[i];
+  }
+  return lh;
+}
+mat loglik_gda::diaghessgradpara() { /* :203-211 */
+  const u64 N = obssd.size();
+  mat t2 = obssd_gradpara;
+  for (u64 c = 0; c < t2.nc; ++c)
+    for (u64 i = 0; i < N; ++i) t2(i, c) *= (1 / (obssd[i] * obssd[i])) * (-2 / obssd[i]);
+  return ob.sqtmmm(terms, t2);
+}
+
+/* ---- pred_gda ---- */
+pred_gda::pred_gda(const loglik_gda& loglik) : om(loglik.om), para(loglik.para), terms(loglik.terms) { /* :249-266 */
+  nthreads = (int)loglik.ob.nthreads;
+  doda = loglik.doda;
+  coeff = loglik.coeff;
+  if (coeff.size() != terms.nr) coeff.assign(terms.nr, 0.0);
+  ob.reset(new outerbase(om, loglik.x, false));
+  ob->nthreads = nthreads;
+  if (!loglik.didnotothess) {
+    coeffvar.resize(loglik.totdiaghess.size());
+    for (u64 i = 0; i < coeffvar.size(); ++i) coeffvar[i] = 1 / loglik.totdiaghess[i];
+  } else coeffvar.assign(coeff.size(), 0.0);
+}
+void pred_gda::update(const mat& x_) { ob.reset(new outerbase(om, x_, false)); ob->nthreads = nthreads; } /* :268-272 */
+vec pred_gda::mean() const { vec o; ob->mm(o, terms, coeff); return o; }                                   /* :273-275 */
+vec pred_gda::var() const { /* :276-282 */
+  vec out = ob->sqmm(terms, coeffvar);
+  const vec rv = doda ? ob->residvar(terms) : vec();
+  for (u64 i = 0; i < out.size(); ++i) { out[i] += std::exp(2 * para[0]); if (doda) out[i] += std::exp(2 * para[1]) * rv[i]; }
+  return out;
 }
 
 /* ---- lpdfvec ---- */

@@ -166,6 +166,8 @@ struct outerbase {
   mat sqtmm_gradhyp(const umat& terms, const vec& a) const;  /* :845-855 */
   vec sqcolsums(const umat& terms) const;                    /* :863-867 */
   mat sqcolsums_gradhyp(const umat& terms) const;            /* :875-879 */
+  vec residvar(const umat& terms) const;                     /* :889-896 */
+  mat residvar_gradhyp(const umat& terms) const;             /* :904-922 */
 };
 
 /* ---- lpdf family: src/fit.h:23-148,236-268 ; src/fit.cpp ; src/lpdfs/ ---- */
@@ -238,6 +240,31 @@ struct loglik_gauss : lpdf { /* src/lpdfs/loglik_gauss.cpp:41-179 */
   u64 nrow() const override { return ob.n_row; }
 };
 
+struct loglik_gda : lpdf { /* src/lpdfs/loglik_gda.cpp:47-239, src/fit.h:272-310: Gaussian likelihood whose noise
+                             variance carries the variance of the terms left out of the basis (obfit stage 1) */
+  const outermod& om;
+  outerbase ob;
+  vec y;
+  mat x;
+  bool doda = true, redostd = true;
+  vec yhat, obssd;
+  mat yhatge, obssd_gradhyp, obssd_gradpara;
+  vec gradtemp, yhattemp, residtemp, residtemp2;
+  loglik_gda(const outermod& om_, const umat& terms_, const vec& y_, const mat& x_);
+  void setnthreads(int k) override;
+  void updateom() override;
+  void updatepara(const vec&) override;
+  void updateterms(const umat&) override;
+  void update(const vec& coeff_) override;
+  vec hessmult(const vec& g) override;
+  vec diaghess() override;
+  mat diaghessgradhyp() override;
+  mat diaghessgradpara() override;
+  void buildstd();
+  u64 nhyp() const override { return ob.n_hyp; }
+  u64 nrow() const override { return ob.n_row; }
+};
+
 struct lpdfvec : lpdf { /* src/fit.h:93-148 ; src/fit.cpp:174-267,310-428,557-607 */
   double val_margadj = 0;
   vec gradhyp_margadj, gradpara_margadj;
@@ -277,6 +304,20 @@ struct pred_gauss { /* src/lpdfs/loglik_gauss.cpp:196-227 */
   vec coeff, coeffvar;
   std::unique_ptr<outerbase> ob;
   pred_gauss(const loglik_gauss& loglik);
+  void update(const mat& x_);
+  vec mean() const;
+  vec var() const;
+};
+
+struct pred_gda { /* src/lpdfs/loglik_gda.cpp:249-283 */
+  const outermod& om;
+  vec para;
+  umat terms;
+  int nthreads = 0;
+  bool doda = true;
+  vec coeff, coeffvar;
+  std::unique_ptr<outerbase> ob;
+  pred_gda(const loglik_gda& loglik);
   void update(const mat& x_);
   vec mean() const;
   vec var() const;

@@ -36,7 +36,7 @@ struct orc_lpdf {
   std::unique_ptr<lpdf> p;
   int kind; /* 0 loglik_gauss, 1 logpr_gauss, 2 lpdfvec */
 };
-struct orc_predictor { std::unique_ptr<pred_gauss> p; uint64_t d; };
+struct orc_predictor { std::unique_ptr<pred_gauss> p; std::unique_ptr<pred_gda> pg; uint64_t d; };
 
 static umat to_umat(const uint64_t* t, uint64_t K, uint64_t d) {
   umat m(K, d);
@@ -284,6 +284,12 @@ int orc_outerbase_tmm_mat(orc_outerbase* ob, int sq, const uint64_t* terms, uint
   std::copy(o.a.begin(), o.a.end(), out);
   ORC_CATCH
 }
+int orc_outerbase_residvar(orc_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
+  ORC_TRY vec o = ob->ob->residvar(to_umat(terms, K, ob->ob->d)); std::copy(o.begin(), o.end(), out); ORC_CATCH
+}
+int orc_outerbase_residvar_gradhyp(orc_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
+  ORC_TRY mat o = ob->ob->residvar_gradhyp(to_umat(terms, K, ob->ob->d)); std::copy(o.a.begin(), o.a.end(), out); ORC_CATCH
+}
 int orc_outerbase_set_terms(orc_outerbase* ob, const uint64_t* terms, uint64_t K) { ORC_TRY ob->terms = to_umat(terms, K, ob->ob->d); ORC_CATCH }
 int orc_outerbase_mm_dev(orc_outerbase* ob, int sq, const double* a, double* out) { ORC_TRY mm_impl(*ob->ob, sq, ob->terms, a, out); ORC_CATCH }
 int orc_outerbase_tmm_dev(orc_outerbase* ob, int sq, const double* a, double* out) { ORC_TRY tmm_impl(*ob->ob, sq, ob->terms, a, out); ORC_CATCH }
@@ -387,6 +393,15 @@ int orc_loglik_gauss_create(orc_ctx*, orc_outermod* om, const uint64_t* terms, u
   *out = h;
   ORC_CATCH
 }
+int orc_loglik_gda_create(orc_ctx*, orc_outermod* om, const uint64_t* terms, uint64_t K, const double* y,
+                          const double* x, uint64_t N, orc_lpdf** out) {
+  ORC_TRY
+  auto* h = new orc_lpdf();
+  h->kind = 3;
+  h->p.reset(new loglik_gda(om->om, to_umat(terms, K, om->om.d), vec(y, y + N), to_mat(x, N, om->om.d)));
+  *out = h;
+  ORC_CATCH
+}
 int orc_logpr_gauss_create(orc_ctx*, orc_outermod* om, const uint64_t* terms, uint64_t K, orc_lpdf** out) {
   ORC_TRY
   auto* h = new orc_lpdf();
@@ -436,6 +451,10 @@ int orc_lpdf_set_flag(orc_lpdf* l, const char* which, int value) {
     auto* v = dynamic_cast<lpdfvec*>(l->p.get());
     if (!v) throw std::invalid_argument("domarg is a field of lpdfvec");
     v->domargadj = value;
+  } else if (w == "dodiag") { /* R field name of loglik_gda::doda, interfaceR.cpp:748 */
+    auto* v = dynamic_cast<loglik_gda*>(l->p.get());
+    if (!v) throw std::invalid_argument("dodiag is a field of loglik_gda");
+    v->doda = value; v->redostd = true;
   } else throw std::invalid_argument("unknown flag " + w);
   ORC_CATCH
 }
@@ -456,9 +475,9 @@ int orc_lpdf_get(orc_lpdf* l, const char* which, double* out, uint64_t* n) {
   else if (w == "totdiaghess") v = l->p->totdiaghess;
   else if (w == "cg_iters") v = {double(l->p->cg_iters)};
   else if (w == "yhat") {
-    auto* g = dynamic_cast<loglik_gauss*>(l->p.get());
-    if (!g) throw std::invalid_argument("yhat is a field of loglik_gauss");
-    v = g->yhat;
+    if (auto* g = dynamic_cast<loglik_gauss*>(l->p.get())) v = g->yhat;
+    else if (auto* g2 = dynamic_cast<loglik_gda*>(l->p.get())) v = g2->yhat;
+    else throw std::invalid_argument("yhat is a field of loglik_gauss / loglik_gda");
   } else if (w == "coeffsd") {
     auto* g = dynamic_cast<logpr_gauss*>(l->p.get());
     if (!g) throw std::invalid_argument("coeffsd is a field of logpr_gauss");
@@ -472,17 +491,18 @@ int orc_lpdf_set_coeff(orc_lpdf* l, const double* coeff, uint64_t K) { ORC_TRY l
 
 int orc_predictor_create(orc_lpdf* loglik, orc_predictor** out) {
   ORC_TRY
-  auto* g = dynamic_cast<loglik_gauss*>(loglik->p.get());
-  if (!g) throw std::invalid_argument("cannot produce a predictor from this obj.");
   auto* h = new orc_predictor();
-  h->p.reset(new pred_gauss(*g));
-  h->d = g->om.d;
+  if (auto* g = dynamic_cast<loglik_gauss*>(loglik->p.get())) { h->p.reset(new pred_gauss(*g)); h->d = g->om.d; }
+  else if (auto* g2 = dynamic_cast<loglik_gda*>(loglik->p.get())) { h->pg.reset(new pred_gda(*g2)); h->d = g2->om.d; }
+  else { delete h; throw std::invalid_argument("cannot produce a predictor from this obj."); }
   *out = h;
   ORC_CATCH
 }
 int orc_predictor_destroy(orc_predictor* p) { delete p; return ORC_OK; }
-int orc_predictor_update(orc_predictor* p, const double* x, uint64_t N) { ORC_TRY p->p->update(to_mat(x, N, p->d)); ORC_CATCH }
-int orc_predictor_mean(orc_predictor* p, double* out) { ORC_TRY vec o = p->p->mean(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
-int orc_predictor_var(orc_predictor* p, double* out) { ORC_TRY vec o = p->p->var(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
+int orc_predictor_update(orc_predictor* p, const double* x, uint64_t N) {
+  ORC_TRY if (p->p) p->p->update(to_mat(x, N, p->d)); else p->pg->update(to_mat(x, N, p->d)); ORC_CATCH
+}
+int orc_predictor_mean(orc_predictor* p, double* out) { ORC_TRY vec o = p->p ? p->p->mean() : p->pg->mean(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
+int orc_predictor_var(orc_predictor* p, double* out) { ORC_TRY vec o = p->p ? p->p->var() : p->pg->var(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
 
 } // extern "C"

@@ -10,7 +10,7 @@ import os
 import subprocess
 from pathlib import Path
 
-from .binding import (Library, getpara, gethyp, header_symbols, loglik_gauss, logpr_gauss, lpdf, lpdfvec,  # noqa: F401
+from .binding import (Library, getpara, gethyp, header_symbols, loglik_gauss, loglik_gda, logpr_gauss, lpdf, lpdfvec,  # noqa: F401
                       outerbase, outermod, predictor, setcovfs, setknot)
 
 ROOT = Path(__file__).resolve().parent

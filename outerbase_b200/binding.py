@@ -174,6 +174,9 @@ class Library:
     def loglik_gauss(self, om, terms, y, x):
         return loglik_gauss(self, om, terms, y, x)
 
+    def loglik_gda(self, om, terms, y, x):
+        return loglik_gda(self, om, terms, y, x)
+
     def logpr_gauss(self, om, terms):
         return logpr_gauss(self, om, terms)
 
@@ -481,6 +484,20 @@ class outerbase(_Handle):
     def sqtmmm(self, terms, a):
         return self._tmm(1, terms, a)
 
+    def residvar(self, terms):
+        """outerbase::residvar, src/modandbase.cpp:889-896."""
+        t = _terms(terms)
+        out = np.empty(self.n_row)
+        self._lib.call("outerbase_residvar", self._h, _p(t), _u(t.shape[0]), _p(out))
+        return out
+
+    def residvar_gradhyp(self, terms):
+        """outerbase::residvar_gradhyp, src/modandbase.cpp:904-922."""
+        t = _terms(terms)
+        out = np.empty((self.n_row, self._om.sizes()[1]), order="F")
+        self._lib.call("outerbase_residvar_gradhyp", self._h, _p(t), _u(t.shape[0]), _p(out))
+        return out
+
     def sqmm_gradhyp(self, terms, a):
         return self._mmge(1, terms, a)[1]
 
@@ -623,6 +640,21 @@ class loglik_gauss(lpdf):
         lib.call("loglik_gauss_create", lib.ctx, om._h, _p(t), _u(t.shape[0]), _p(y), _p(x), _u(y.size), C.byref(self._h))
 
     yhat = property(lambda s: s._get("yhat"))
+
+
+class loglik_gda(lpdf):
+    """new(loglik_gda, om, terms, y, x) -- src/lpdfs/loglik_gda.cpp:47, src/interfaceR.cpp:745-750."""
+
+    def __init__(self, lib, om, terms, y, x):
+        super().__init__(lib)
+        self._om = om
+        t, y, x = _terms(terms), _f64(y), _f64(x)
+        if x.shape[0] != y.size:
+            raise ValueError("x and y dims do not align")
+        lib.call("loglik_gda_create", lib.ctx, om._h, _p(t), _u(t.shape[0]), _p(y), _p(x), _u(y.size), C.byref(self._h))
+
+    yhat = property(lambda s: s._get("yhat"))
+    dodiag = property(fset=lambda s, v: s._flag("dodiag", v))
 
 
 class logpr_gauss(lpdf):

@@ -26,7 +26,7 @@ struct ob_ctx { obd::Ctx c; explicit ob_ctx(int dev) : c(dev) {} };
 struct ob_outermod { obh::OuterMod om; };
 struct ob_outerbase { ob_ctx* ctx; std::unique_ptr<obe::OuterBase> ob; };
 struct ob_lpdf { ob_ctx* ctx; std::unique_ptr<obe::Lpdf> p; };
-struct ob_predictor { std::unique_ptr<obe::PredGauss> p; };
+struct ob_predictor { std::unique_ptr<obe::PredGauss> p; std::unique_ptr<obe::PredGda> pg; };
 
 static void need(const void* p, const char* what) { if (!p) throw std::invalid_argument(std::string("null ") + what); }
 
@@ -204,6 +204,12 @@ int ob_outerbase_mm_mat(ob_outerbase* ob, int sq, const uint64_t* terms, uint64_
 int ob_outerbase_tmm_mat(ob_outerbase* ob, int sq, const uint64_t* terms, uint64_t K, const double* A, uint64_t C, double* out) {
   OB_TRY ob->ob->tmm_mat(sq, terms, K, A, C, out); OB_CATCH
 }
+int ob_outerbase_residvar(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
+  OB_TRY need(ob, "ob"); ob->ob->residvar(terms, K, out); OB_CATCH
+}
+int ob_outerbase_residvar_gradhyp(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
+  OB_TRY need(ob, "ob"); ob->ob->residvar_gradhyp(terms, K, out); OB_CATCH
+}
 int ob_outerbase_set_terms(ob_outerbase* ob, const uint64_t* terms, uint64_t K) {
   OB_TRY
   obe::OuterBase& b = *ob->ob;
@@ -352,6 +358,16 @@ int ob_loglik_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, 
   *out = h;
   OB_CATCH
 }
+int ob_loglik_gda_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K, const double* y, const double* x,
+                         uint64_t N, ob_lpdf** out) {
+  OB_TRY
+  need(ctx, "ctx"); need(om, "om");
+  auto* h = new ob_lpdf();
+  h->ctx = ctx;
+  try { h->p.reset(new obe::LoglikGda(ctx->c, &om->om, terms, K, y, x, N)); } catch (...) { delete h; throw; }
+  *out = h;
+  OB_CATCH
+}
 int ob_logpr_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K, ob_lpdf** out) {
   OB_TRY
   need(om, "om");
@@ -399,6 +415,10 @@ int ob_lpdf_set_flag(ob_lpdf* l, const char* which, int value) {
     auto* v = dynamic_cast<obe::LpdfVec*>(l->p.get());
     if (!v) throw std::invalid_argument("domarg is a field of lpdfvec");
     v->domargadj = value;
+  } else if (w == "dodiag") { /* R field name of loglik_gda::doda, interfaceR.cpp:748 */
+    auto* v = dynamic_cast<obe::LoglikGda*>(l->p.get());
+    if (!v) throw std::invalid_argument("dodiag is a field of loglik_gda");
+    v->doda = value; v->redostd = true;
   } else throw std::invalid_argument("unknown flag " + w);
   OB_CATCH
 }
@@ -418,9 +438,9 @@ int ob_lpdf_get(ob_lpdf* l, const char* which, double* out, uint64_t* n) {
   else if (w == "totdiaghess") v = l->p->totdiaghess;
   else if (w == "cg_iters") v = {double(l->p->cg_iters)};
   else if (w == "yhat") {
-    auto* g = dynamic_cast<obe::LoglikGauss*>(l->p.get());
-    if (!g) throw std::invalid_argument("yhat is a field of loglik_gauss");
-    v = g->get_yhat();
+    if (auto* g = dynamic_cast<obe::LoglikGauss*>(l->p.get())) v = g->get_yhat();
+    else if (auto* g2 = dynamic_cast<obe::LoglikGda*>(l->p.get())) v = g2->yhat;
+    else throw std::invalid_argument("yhat is a field of loglik_gauss / loglik_gda");
   } else if (w == "coeffsd") {
     auto* g = dynamic_cast<obe::LogprGauss*>(l->p.get());
     if (!g) throw std::invalid_argument("coeffsd is a field of logpr_gauss");
@@ -434,16 +454,18 @@ int ob_lpdf_set_coeff(ob_lpdf* l, const double* coeff, uint64_t K) { OB_TRY l->p
 
 int ob_predictor_create(ob_lpdf* loglik, ob_predictor** out) {
   OB_TRY
-  auto* g = dynamic_cast<obe::LoglikGauss*>(loglik->p.get());
-  if (!g) throw std::invalid_argument("cannot produce a predictor from this obj.");
   auto* h = new ob_predictor();
-  try { h->p.reset(new obe::PredGauss(*g)); } catch (...) { delete h; throw; }
+  try {
+    if (auto* g = dynamic_cast<obe::LoglikGauss*>(loglik->p.get())) h->p.reset(new obe::PredGauss(*g));
+    else if (auto* g2 = dynamic_cast<obe::LoglikGda*>(loglik->p.get())) h->pg.reset(new obe::PredGda(*g2));
+    else throw std::invalid_argument("cannot produce a predictor from this obj.");
+  } catch (...) { delete h; throw; }
   *out = h;
   OB_CATCH
 }
 int ob_predictor_destroy(ob_predictor* p) { OB_TRY delete p; OB_CATCH }
-int ob_predictor_update(ob_predictor* p, const double* x, uint64_t N) { OB_TRY p->p->update(x, N); OB_CATCH }
-int ob_predictor_mean(ob_predictor* p, double* out) { OB_TRY p->p->mean(out); OB_CATCH }
-int ob_predictor_var(ob_predictor* p, double* out) { OB_TRY p->p->var(out); OB_CATCH }
+int ob_predictor_update(ob_predictor* p, const double* x, uint64_t N) { OB_TRY if (p->p) p->p->update(x, N); else p->pg->update(x, N); OB_CATCH }
+int ob_predictor_mean(ob_predictor* p, double* out) { OB_TRY if (p->p) p->p->mean(out); else p->pg->mean(out); OB_CATCH }
+int ob_predictor_var(ob_predictor* p, double* out) { OB_TRY if (p->p) p->p->var(out); else p->pg->var(out); OB_CATCH }
 
 } // extern "C"

@@ -498,6 +498,25 @@ struct OuterBase {
     tmm_mat_dev(terms, K, sq, tmpN2.p, ld, C, tmpK.p);
     d2h(out, tmpK.p, K * C);
   }
+  /* outerbase::residvar / residvar_gradhyp, modandbase.cpp:889-922 (assume a correlation function) */
+  void residvar(const u64* terms, u64 K, double* out /* N */) {
+    if (!om) throw std::logic_error("residvar needs the outermod");
+    std::vector<double> varc(K);
+    om->getvar(terms, K, varc.data());
+    mm(1, terms, K, varc.data(), out);
+    for (u64 i = 0; i < N; ++i) out[i] = 1 - out[i];
+  }
+  void residvar_gradhyp(const u64* terms, u64 K, double* out /* N x H */) {
+    if (!om) throw std::logic_error("residvar_gradhyp needs the outermod");
+    std::vector<double> varc(K), l2(K * H), l3(N * H);
+    om->getvar(terms, K, varc.data());
+    mm_gradhyp(1, terms, K, varc.data(), nullptr, out);
+    om->getlvar_gradhyp(terms, K, l2.data());
+    for (u64 h = 0; h < H; ++h)
+      for (u64 k = 0; k < K; ++k) l2[k + h * K] *= varc[k];
+    mm_mat(1, terms, K, l2.data(), H, l3.data());
+    for (u64 i = 0; i < N * H; ++i) out[i] = -out[i] - l3[i];
+  }
   void getmat(const u64* terms, u64 K, double* out) {
     obd::DevProgram* pr = program(terms, K, -1);
     tmpP.ensure(ld * K);
@@ -820,6 +839,147 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
   u64 nrow() const override { return N; }
 };
 
+/* loglik_gda (src/lpdfs/loglik_gda.cpp:47-239): the stage-1 likelihood of obfit, built on a <= 3*numb-row subsample
+ * (R/fitting.R:79-84).  Every Phi-type product runs on the GPU kernels through the outerbase operators; the
+ * N-vector bookkeeping around them (per-row noise scale and its derivatives) follows the reference on the host. */
+struct LoglikGda : Lpdf {
+  Ctx& ctx;
+  const OuterMod* om;
+  OuterBase ob;
+  std::vector<double> x_host, y;
+  u64 N = 0;
+  bool doda = true, redostd = true;
+  std::vector<double> yhat, obssd, yhatge, obssd_gradhyp, obssd_gradpara, residtemp, residtemp2;
+
+  LoglikGda(Ctx& c, const OuterMod* om_, const u64* t, u64 K, const double* yh, const double* xh, u64 N_)
+      : ctx(c), om(om_), ob(c, om_, xh, N_, true), N(N_) {
+    if (ctx.nranks > 1) throw std::logic_error("loglik_gda is the single-rank subsample model of obfit stage 1");
+    d = om->d; npara = 2;
+    terms.assign(t, t + K * d);
+    nterms = K;
+    x_host.assign(xh, xh + N * d);
+    y.assign(yh, yh + N);
+    para0 = {0.5 * std::log(0.01 * LoglikGauss::arma_var(yh, N)), 0.0};
+    paravar = {4, 4};
+    para = para0;
+    buildstd();
+  }
+  void setnthreads(int k) override { ob.nthreads = k; }
+  void updateom() override { ob.build(); if (doda) redostd = true; }
+  void updatepara(const double* p, u64 n) override { para.assign(p, p + n); redostd = true; }
+  void updateterms(const u64* t, u64 K) override { terms.assign(t, t + K * d); nterms = K; if (doda) redostd = true; }
+  static double dot2(const double* a, const double* b, u64 n) { /* Armadillo's two-accumulator dot */
+    double s1 = 0, s2 = 0;
+    u64 j;
+    for (j = 1; j < n; j += 2) { s1 += a[j - 1] * b[j - 1]; s2 += a[j] * b[j]; }
+    if ((j - 1) < n) s1 += a[j - 1] * b[j - 1];
+    return s1 + s2;
+  }
+  void buildstd() { /* :217-236 */
+    if (redostd) {
+      const u64 H = ob.H, K = nterms;
+      std::vector<double> rterms(N);
+      ob.residvar(terms.data(), K, rterms.data());
+      obssd.resize(N);
+      for (u64 i = 0; i < N; ++i) {
+        double v = std::exp(2 * para[0]);
+        if (doda) v += std::exp(2 * para[1]) * rterms[i];
+        obssd[i] = std::sqrt(v);
+      }
+      if (doda) {
+        obssd_gradhyp.resize(N * H);
+        ob.residvar_gradhyp(terms.data(), K, obssd_gradhyp.data());
+        for (u64 h = 0; h < H; ++h)
+          for (u64 i = 0; i < N; ++i) obssd_gradhyp[i + h * N] *= (std::exp(2 * para[1]) * 0.5) / obssd[i];
+      }
+      obssd_gradpara.assign(N * 2, 0.0);
+      for (u64 i = 0; i < N; ++i) {
+        obssd_gradpara[i] = std::exp(2 * para[0]) / obssd[i];
+        obssd_gradpara[i + N] = doda ? std::exp(2 * para[1]) * rterms[i] / obssd[i] : 0.0;
+      }
+    }
+    redostd = false;
+  }
+  void update(const std::vector<double>& c) override { /* :116-149 */
+    coeff = c;
+    const u64 K = nterms, H = ob.H;
+    if (c.size() != K) throw std::range_error("coeff must have one entry per term");
+    yhat.resize(N);
+    if (compute_gradhyp) { yhatge.resize(N * H); ob.mm_gradhyp(0, terms.data(), K, coeff.data(), yhat.data(), yhatge.data()); }
+    else ob.mm(0, terms.data(), K, coeff.data(), yhat.data());
+    buildstd();
+    residtemp.resize(N); residtemp2.resize(N);
+    for (u64 i = 0; i < N; ++i) { residtemp[i] = (yhat[i] - y[i]) / obssd[i]; residtemp2[i] = residtemp[i] * residtemp[i]; }
+    if (compute_val) {
+      std::vector<double> t(N);
+      for (u64 i = 0; i < N; ++i) t[i] = std::log(obssd[i]);
+      val = -0.5 * obh::sum2(residtemp2.data(), N) - obh::sum2(t.data(), N);
+    }
+    if (compute_grad) {
+      std::vector<double> inv(N);
+      for (u64 i = 0; i < N; ++i) { residtemp[i] = -1. * (residtemp[i] / obssd[i]); residtemp2[i] /= obssd[i]; inv[i] = 1 / obssd[i]; }
+      grad.resize(K);
+      ob.tmm(0, terms.data(), K, residtemp.data(), grad.data());
+      if (compute_gradhyp) {
+        gradhyp.assign(H, 0.0);
+        for (u64 h = 0; h < H; ++h) {
+          gradhyp[h] = dot2(residtemp.data(), yhatge.data() + h * N, N);
+          if (doda) {
+            gradhyp[h] += dot2(residtemp2.data(), obssd_gradhyp.data() + h * N, N);
+            gradhyp[h] -= dot2(inv.data(), obssd_gradhyp.data() + h * N, N);
+          }
+        }
+      }
+      if (compute_gradpara) {
+        gradpara.assign(2, 0.0);
+        for (u64 q = 0; q < 2; ++q) {
+          gradpara[q] = dot2(residtemp2.data(), obssd_gradpara.data() + q * N, N);
+          gradpara[q] -= dot2(inv.data(), obssd_gradpara.data() + q * N, N);
+        }
+      }
+    }
+  }
+  std::vector<double> hessmult(const std::vector<double>& g) override { /* :156-164 */
+    const u64 K = nterms;
+    std::vector<double> yt(N), o(K);
+    ob.mm(0, terms.data(), K, g.data(), yt.data());
+    for (u64 i = 0; i < N; ++i) { yt[i] /= obssd[i]; yt[i] /= obssd[i]; }
+    ob.tmm(0, terms.data(), K, yt.data(), o.data());
+    return o;
+  }
+  std::vector<double> diaghess() override { /* :172-175 */
+    std::vector<double> t(N), o(nterms);
+    for (u64 i = 0; i < N; ++i) t[i] = 1 / (obssd[i] * obssd[i]);
+    ob.tmm(1, terms.data(), nterms, t.data(), o.data());
+    return o;
+  }
+  std::vector<double> diaghessgradhyp() override { /* :182-196 */
+    const u64 K = nterms, H = ob.H;
+    std::vector<double> temp(N), lh(K * H);
+    for (u64 i = 0; i < N; ++i) temp[i] = 1 / (obssd[i] * obssd[i]);
+    ob.tmm_gradhyp(1, terms.data(), K, temp.data(), nullptr, lh.data());
+    for (u64 i = 0; i < N; ++i) temp[i] *= -2 / obssd[i];
+    if (doda) {
+      std::vector<double> t2(obssd_gradhyp), add(K * H);
+      for (u64 h = 0; h < H; ++h)
+        for (u64 i = 0; i < N; ++i) t2[i + h * N] *= temp[i];
+      ob.tmm_mat(1, terms.data(), K, t2.data(), H, add.data());
+      for (u64 i = 0; i < K * H; ++i) lh[i] += add[i];
+    }
+    return lh;
+  }
+  std::vector<double> diaghessgradpara() override { /* :203-211 */
+    const u64 K = nterms;
+    std::vector<double> t2(obssd_gradpara), o(K * 2);
+    for (u64 q = 0; q < 2; ++q)
+      for (u64 i = 0; i < N; ++i) t2[i + q * N] *= (1 / (obssd[i] * obssd[i])) * (-2 / obssd[i]);
+    ob.tmm_mat(1, terms.data(), K, t2.data(), 2, o.data());
+    return o;
+  }
+  u64 nhyp() const override { return ob.H; }
+  u64 nrow() const override { return N; }
+};
+
 struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
   double val_margadj = 0;
   std::vector<double> gradhyp_margadj, gradpara_margadj;
@@ -970,6 +1130,32 @@ struct PredGauss { /* loglik_gauss.cpp:196-227 */
     ob->mm(1, terms.data(), K, coeffvar.data(), out);
     const double c = std::exp(2 * para[0]);
     for (u64 i = 0; i < ob->N; ++i) out[i] += c;
+  }
+};
+
+struct PredGda { /* loglik_gda.cpp:249-283 */
+  Ctx& ctx;
+  const OuterMod* om;
+  std::vector<double> para, coeff, coeffvar;
+  std::vector<u64> terms;
+  u64 K, d;
+  bool doda;
+  std::unique_ptr<OuterBase> ob;
+  PredGda(LoglikGda& lk) : ctx(lk.ctx), om(lk.om), para(lk.para), coeff(lk.coeff), terms(lk.terms), K(lk.nterms), d(lk.d), doda(lk.doda) {
+    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false));
+    if (coeff.size() != K) coeff.assign(K, 0.0);
+    if (!lk.didnotothess) {
+      coeffvar.resize(lk.totdiaghess.size());
+      for (u64 i = 0; i < coeffvar.size(); ++i) coeffvar[i] = 1 / lk.totdiaghess[i];
+    } else coeffvar.assign(coeff.size(), 0.0);
+  }
+  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false)); }
+  void mean(double* out) { ob->mm(0, terms.data(), K, coeff.data(), out); }
+  void var(double* out) {
+    ob->mm(1, terms.data(), K, coeffvar.data(), out);
+    std::vector<double> rv(ob->N);
+    if (doda) ob->residvar(terms.data(), K, rv.data());
+    for (u64 i = 0; i < ob->N; ++i) { out[i] += std::exp(2 * para[0]); if (doda) out[i] += std::exp(2 * para[1]) * rv[i]; }
   }
 };
 

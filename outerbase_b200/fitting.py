@@ -12,8 +12,8 @@ on both.  Nothing N-sized happens in this file: every objective evaluation is
   lpdfwrapper   R/outersupport.R:209-226  negated log-posterior and its gradient in (hyp, para)
   genknotlist   R/fitting.R:177-185       type-7 quantile knots
   getsteps      R/fitting.R:188-195
-  obfit_gauss   R/fitting.R:100-136       the stage-2 loop of obfit (loglik_gauss + BFGS_lpdf); stage 1
-                                          (loglik_gda, R/fitting.R:76-98) is outside this round's scope
+  obfit         R/fitting.R:27-137        both stages: loglik_gda on a subsample, then loglik_gauss on all rows
+  obfit_gauss   R/fitting.R:100-136       the stage-2 loop alone, started from the constructor defaults
   obpred        R/fitting.R:149-155
 """
 from __future__ import annotations
@@ -221,6 +221,74 @@ def obfit_gauss(lib, x, y, numb=100, covnames=None, hyp=None, numberopts=2, verb
         optinfo = BFGS_lpdf(om, logpdf, verbose=verbose, B=optinfo["B"], lr=optinfo["lr"] / 2)
     return dict(y_cent=y_cent, y_sca=y_sca, om=om, terms=terms, logpdf=logpdf, loglik=loglik, logpr=logpr,
                 predobj=lib.predictor(loglik), optinfo=optinfo)
+
+
+def obfit(lib, x, y, numb=100, verbose=0, covnames=None, hyp=None, numberopts=2, nthreads=None, seed=0):
+    """obfit, R/fitting.R:27-137.  The row subsample of stage 1 is drawn with numpy's generator (`seed`) where the
+    reference uses R's `sample`; everything else follows the R code line by line."""
+    x = np.asfortranarray(np.asarray(x, dtype=float))
+    y = np.asarray(y, dtype=float)
+    n, d = x.shape
+    if n != y.size:
+        raise ValueError("x and y dims do not align")
+    if n < d:
+        raise ValueError("dimension larger than sample size has not been tested")
+    if d == 1:
+        raise ValueError("dimension must be larger than 1")
+    if d == 2:
+        raise ValueError("dimension 2 has not been tested")
+    if numb < 2 * d:
+        raise ValueError("number of basis functions should be less than twice the dimension")
+    if numb > 100000:
+        raise ValueError("number of basis functions is beyond testing")
+    # R/fitting.R:33 stops for n > 1e6 (SURVEY A9.ii); the GPU path has no such limit
+    y_cent, y_sca = float(y.mean()), float(y.std(ddof=1))
+    ys = (y - y_cent) / y_sca
+    covnames = list(covnames) if covnames is not None else ["mat25pow"] * d
+    if len(covnames) != d:
+        raise ValueError("cov names must be same size as columns in x")
+    om = lib.outermod()
+    om.setcovfs(covnames)
+    if hyp is not None and len(hyp) == gethyp(om).size:
+        om.updatehyp(hyp)
+    om.setknot(genknotlist([40] * d, x))  # 40 knot point for each dim
+    # ---- stage 1: few terms, row subsample, loglik_gda (R/fitting.R:76-98)
+    numbr = min(n // 2, numb, 80 * d)
+    terms = om.selectterms(numbr)
+    ssr = min(n, 3 * numbr)
+    logpr = lib.logpr_gauss(om, terms)
+    subset = np.sort(np.random.default_rng(seed).choice(n, size=ssr, replace=False))
+    loglik = lib.loglik_gda(om, terms, ys[subset], np.asfortranarray(x[subset]))
+    loglik.dodiag = True
+    logpdf = lib.lpdfvec(logpr, loglik)
+    if nthreads is not None:
+        logpdf.setnthreads(int(math.ceil(nthreads)))
+    if verbose > 0:
+        print("doing partial optimization")
+    optinfo = BFGS_lpdf(om, logpdf, verbose=verbose, cgsteps=100)
+    # ---- stage 2: all rows, loglik_gauss (R/fitting.R:100-136)
+    terms = om.selectterms(numb)
+    bassize = np.ceil(np.maximum(16, np.minimum(70, 2 * np.asarray(terms).max(axis=0)))).astype(int)
+    om.setknot(genknotlist(bassize, x))
+    loglik_faster = lib.loglik_gauss(om, terms, ys, x)
+    logpdf_faster = lib.lpdfvec(logpr, loglik_faster)
+    logpdf_faster.domarg = True
+    B = np.asarray(optinfo["B"])[:-1, :-1]          # one fewer para, so we strip that one off
+    B = ssr / n * B                                  # decrease scale
+    logpdf_faster.updatepara(getpara(logpdf)[:2])
+    if nthreads is not None:
+        logpdf_faster.setnthreads(int(math.ceil(nthreads)))
+    lr = optinfo["lr"]
+    for k in range(numberopts):
+        if verbose > 0:
+            print("doing optimization", k + 1)
+        terms = om.selectterms(numb)
+        logpdf_faster.updateterms(terms)
+        optinfo = BFGS_lpdf(om, logpdf_faster, verbose=verbose, B=B, lr=lr / 2,
+                            cgsteps=getsteps(numb, n, float(np.var(ys, ddof=1)) / math.exp(2 * getpara(logpdf_faster)[1])))
+        B, lr = optinfo["B"], optinfo["lr"]
+    return dict(y_cent=y_cent, y_sca=y_sca, om=om, terms=terms, logpdf=logpdf_faster, loglik=loglik_faster, logpr=logpr,
+                predobj=lib.predictor(loglik_faster), optinfo=optinfo, stage1=dict(logpdf=logpdf, loglik=loglik, rows=subset))
 
 
 def obpred(obmodel, x):

@@ -99,3 +99,34 @@ def test_obfit_gauss_and_obpred_on_gpu(gpu):
     yt = borehole8d(xt)
     assert np.all(pred["var"] > 0)
     assert np.mean((pred["mean"] - yt) ** 2) < 0.02 * np.var(yt)
+
+
+def test_obfit_both_stages_on_the_oracle(oracle):
+    """obfit (R/fitting.R:27-137) end to end on the CPU oracle: stage 1 on loglik_gda, stage 2 on loglik_gauss."""
+    rng = np.random.default_rng(4)
+    x = np.asfortranarray(rng.uniform(size=(400, 3)))
+    y = np.sin(3 * x[:, 0]) + x[:, 1] * x[:, 2] + 0.5 * x[:, 1] ** 2
+    model = fitting.obfit(oracle, x, y, numb=30, covnames=["mat25pow"] * 3, numberopts=1)
+    xt = np.asfortranarray(rng.uniform(size=(200, 3)))
+    pred = fitting.obpred(model, xt)
+    yt = np.sin(3 * xt[:, 0]) + xt[:, 1] * xt[:, 2] + 0.5 * xt[:, 1] ** 2
+    assert np.all(pred["var"] > 0)
+    assert np.mean((pred["mean"] - yt) ** 2) < 0.05 * np.var(yt)
+    assert model["stage1"]["rows"].size == min(400, 3 * 30)
+
+
+@pytest.mark.gpu
+def test_obfit_gpu_matches_oracle(gpu, oracle):
+    """The whole of obfit, one driver over both libraries: same subsample, same BFGS control flow."""
+    rng = np.random.default_rng(9)
+    x = np.asfortranarray(rng.uniform(size=(600, 3)))
+    y = np.sin(3 * x[:, 0]) + x[:, 1] * x[:, 2] + 0.5 * x[:, 1] ** 2
+    xt = np.asfortranarray(rng.uniform(size=(150, 3)))
+    res = {}
+    for name, lib in (("gpu", gpu), ("oracle", oracle)):
+        model = fitting.obfit(lib, x, y, numb=40, covnames=["mat25pow"] * 3, numberopts=1, seed=3)
+        res[name] = (fitting.gethyp(model["om"]), fitting.getpara(model["logpdf"]), fitting.obpred(model, xt), model["optinfo"]["optid"]["val"])
+    g, o = res["gpu"], res["oracle"]
+    assert abs(g[3] - o[3]) <= 1e-5 * abs(o[3])
+    assert relerr(g[0], o[0]) < 1e-3 and relerr(g[1], o[1]) < 1e-3
+    assert relerr(g[2]["mean"], o[2]["mean"]) < 1e-4

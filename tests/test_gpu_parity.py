@@ -303,3 +303,40 @@ def test_full_size_properties(gpu):
     # squared operator against the explicit square on a row sample
     s = ob.sqmm(terms, np.abs(a1))
     assert np.all(s >= 0)
+
+
+@pytest.mark.parametrize("N,K", [(300, 40), (2000, 150)])
+def test_loglik_gda_parity(gpu, oracle, N, K):
+    """loglik_gda (loglik_gda.cpp:47-239), residvar(_gradhyp) (modandbase.cpp:889-922) and pred_gda (:249-283): the
+    stage-1 model of obfit; every Phi-type product on the GPU kernels, same values as the oracle."""
+    out = {}
+    for name, lib in (("g", gpu), ("o", oracle)):
+        om, x, y, terms, rng = make_problem(lib, N, K, covs=["mat25"] * 8, knots=[np.arange(0.001, 0.999, 0.05)] * 8)
+        ob = lib.outerbase(om, x)
+        lk = lib.loglik_gda(om, terms, y, x)
+        lk.compute_gradhyp = True; lk.compute_gradpara = True
+        c = rng.normal(size=K) / 50
+        g = rng.normal(size=K)
+        lk.updatepara([np.log(0.2), -0.5])
+        lk.update(c)
+        vec = lib.lpdfvec(lib.logpr_gauss(om, terms), lk)
+        vec.optcg(0.001, 100)
+        pred = lib.predictor(lk)
+        xn = np.asfortranarray(np.random.default_rng(5).uniform(size=(97, 8)))
+        pred.update(xn)
+        out[name] = dict(rv=ob.residvar(terms), rvg=ob.residvar_gradhyp(terms), val=lk.val, grad=lk.grad, gradhyp=lk.gradhyp,
+                         gradpara=lk.gradpara, yhat=lk.yhat, hm=lk.hessmult(g), dh=lk.diaghess(), dhh=lk.diaghessgradhyp(),
+                         dhp=lk.diaghessgradpara(), vval=vec.val, vcoeff=vec.coeff, iters=vec.cg_iters, vgh=vec.gradhyp,
+                         vgp=vec.gradpara, mean=pred.mean(), var=pred.var())
+    g, o = out["g"], out["o"]
+    assert relerr(g["rv"], o["rv"]) < 1e-9 and relerr(g["rvg"], o["rvg"]) < 1e-8
+    # note: lk.* fields were read after optcg, i.e. at the fitted coefficients with gradients of the final update
+    assert abs(g["val"] - o["val"]) <= 1e-8 * abs(o["val"])
+    assert relerr(g["yhat"], o["yhat"]) < 1e-8
+    assert relerr(g["hm"], o["hm"]) < 1e-8 and relerr(g["dh"], o["dh"]) < 1e-8
+    assert relerr(g["dhh"], o["dhh"]) < 1e-7 and relerr(g["dhp"], o["dhp"]) < 1e-8
+    assert g["iters"] == o["iters"]
+    assert abs(g["vval"] - o["vval"]) <= 1e-8 * abs(o["vval"])
+    assert relerr(g["vcoeff"], o["vcoeff"]) < 1e-8
+    assert relerr(g["vgh"], o["vgh"]) < 1e-6 and relerr(g["vgp"], o["vgp"]) < 1e-7
+    assert relerr(g["mean"], o["mean"]) < 1e-7 and relerr(g["var"], o["var"]) < 1e-7
