@@ -79,6 +79,18 @@ def main():
         tmax, tmin = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         assert torch.equal(tmax, tmin)
+        # hyper-parameter learning on sharded rows (BASELINE config C4's driver): every rank runs the same BFGS_lpdf
+        # control flow on bit-identical objective values; compared with the single-rank oracle run
+        from outerbase_b200 import fitting
+        ref.domarg = True; vec.domarg = True
+        ro = fitting.BFGS_lpdf(omr, ref)
+        rg = fitting.BFGS_lpdf(om, vec)
+        assert abs(rg["optid"]["val"] - ro["optid"]["val"]) <= 1e-6 * abs(ro["optid"]["val"]), (rg["optid"]["val"], ro["optid"]["val"])
+        assert relerr(rg["parlist"]["hyp"], ro["parlist"]["hyp"]) < 1e-4
+        t = torch.tensor([rg["optid"]["val"]], dtype=torch.float64).cuda()
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        assert torch.equal(tmax, tmin)
     else:
         # the reduction loglik_gauss::update needs: grad (K) | ssq | row count, one allreduce
         lk = oracle.loglik_gauss(omr, terms, y[lo:hi], x[lo:hi])
