@@ -164,3 +164,36 @@ def test_spec_full_size_properties(spec):
     spec.set_option("spec", 0)
     assert relerr(ob.matmul(terms, a1), y1) < 1e-13
     assert relerr(ob.tmatmul(terms, r), t1) < 1e-12
+
+
+def test_cluster_multicast_variant_parity(oracle):
+    """The cluster / TMA-multicast variant of phi_t_spec (option mc, off by default) stays correct: run it in a
+    fresh process (the options are read when a module is generated) against the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+from conftest import make_problem, relerr, ORACLE_LIB
+from outerbase_b200.binding import Library
+import outerbase_b200 as obp
+gpu = obp.lib(0)
+gpu.set_option("spec", 1)
+oracle = Library(ORACLE_LIB, "orc_")
+om, x, y, terms, rng = make_problem(oracle, 3000, 200)
+ob = oracle.outerbase(om, x)
+omg, *_ = make_problem(gpu, 3000, 200)
+obg = gpu.outerbase(omg, x)
+src, info = gpu.spec_source(terms)
+assert info["types"] >= 2 and "#define OBS_CL %d" % info["types"] in src, info
+a, r = rng.normal(size=200), rng.normal(size=3000)
+assert relerr(obg.tmatmul(terms, r), ob.tmatmul(terms, r)) < 1e-9
+assert relerr(obg.sqtmm(terms, r), ob.sqtmm(terms, r)) < 1e-9
+assert relerr(obg.matmul(terms, a), ob.matmul(terms, a)) < 1e-9
+print("multicast OK", info)
+'''
+    import os
+    env = dict(os.environ, OB_SPEC_OPTS="1,4,2,60,2,1,4,16,32,3,1,1")  # 2 streams x <=32 terms per CTA type, np=3, mc=1
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                         cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    assert res.returncode == 0 and "multicast OK" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
