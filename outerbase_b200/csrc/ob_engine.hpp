@@ -241,7 +241,7 @@ struct OuterBase {
       e->state = -1;
       e->why = ex.what();
       e->k.reset();
-      if (now) throw; /* asked for explicitly: fail loudly */
+      if (force) throw; /* ob_outerbase_specialize: fail loudly; under a policy the interpreter kernels take over */
       return nullptr;
     }
   }

@@ -50,6 +50,22 @@ def test_spec_degenerate_terms(spec, oracle):
         assert relerr(spec.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
 
 
+def test_unspecialisable_table_falls_back_to_the_interpreter_kernels(spec, oracle):
+    """A table with a duplicated row is refused by the trie compiler: under spec = 1 the products still run (brute-force
+    kernel, bit-exact), the state reads -1, and only an explicit specialize() raises."""
+    o = oracle_basis(oracle, 2000, 60)
+    terms = np.asfortranarray(np.vstack([o["terms"], o["terms"][5:6]]))
+    a = o["rng"].normal(size=61)
+    np.testing.assert_array_equal(spec.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a))
+    omg, x, y, _, rng = make_problem(spec, 500, 30)
+    ob = spec.outerbase(omg, x)
+    t2 = np.asfortranarray(np.vstack([omg.selectterms(30), omg.selectterms(30)[3:4]]))
+    ob.matmul(t2, rng.normal(size=31))
+    assert ob.spec_state(t2) == -1
+    with pytest.raises(RuntimeError):
+        ob.specialize(t2)
+
+
 def test_spec_agrees_with_interpreter_and_state(gpu, oracle):
     """Same object, same inputs: interpreter kernels first, then the specialised ones."""
     om, x, y, terms, rng = make_problem(gpu, 5000, 300)
