@@ -167,6 +167,11 @@ bool spec_uses_cluster(const SpecKernels& k);
 bool device_range_readable(const void* p, size_t bytes);
 void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
 void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
+/* Phi . A on the FP64 tensor cores (phi_am_spec): A is K x C column-major (device), out N x C with leading dimension ldo.
+ * The module is generated and compiled at first use.  Returns false when the tile does not fit (caller: column loop). */
+bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* A, u64 C, double* out, u64 ldo);
+/* coefficient blocks in emit order, columns of odd rows swizzled (ob_spec_scaffold.inc, phi_am_spec) */
+void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nblk, double* out);
 /* explicit Phi (N x K column-major, device), getm_ linalg.cpp:685-715 */
 void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo);
 /* sum of n per-CTA partials, fixed order -> out[0] */

@@ -477,7 +477,12 @@ struct OuterBase {
     std::copy(h.begin() + K, h.end(), outge);
   }
   /* multi right-hand sides: one pass per column for now (DMMA kernel: DESIGN.md "next") */
+  /* prodmm_(mat), linalg.cpp:527-557: eight or more columns run as ONE dense contraction on the FP64 tensor cores
+   * (phi_am_spec) when the table is specialised; otherwise a column loop over the vector kernels */
   void mm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 C, double* out_dev, u64 ldo) {
+    if (C >= 8)
+      if (SpecEntry* e = spec_for(terms, K))
+        if (obd::launch_phi_am_spec(ctx, *e->k, plan(e->pa.get(), sq, -1), A_dev, C, out_dev, ldo)) return;
     for (u64 c = 0; c < C; ++c) mm_dev(terms, K, sq, A_dev + c * K, out_dev + c * ldo);
   }
   void tmm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 lda, u64 C, double* out_dev) {

@@ -133,9 +133,16 @@ struct SpecKernels {
   size_t vec_bytes_a = 0; /* shared-memory copy of the coefficients, slot order */
   size_t smem_a_set = 0, smem_t_set = 0;
   int max_clusters = 0;
+  /* multi right-hand-side module (phi_am_spec), built at first use */
+  cudaLibrary_t libm = nullptr;
+  cudaKernel_t km = nullptr;
+  int nblk = 0, mat_state = 0; /* 0 not built, 1 ready, -1 failed */
+  size_t smem_m_set = 0;
+  DevBuf<double> aperm;
+  obt::Program pa_host; /* copy of the G = 1 program the module is generated from */
   double compile_seconds = 0;
   bool from_cache = false;
-  ~SpecKernels() { if (lib) cudaLibraryUnload(lib); }
+  ~SpecKernels() { if (lib) cudaLibraryUnload(lib); if (libm) cudaLibraryUnload(libm); }
 };
 
 obs::SpecOptions spec_default_options() {
@@ -155,6 +162,7 @@ std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const ob
   auto k = std::make_shared<SpecKernels>();
   k->opt = opt; k->types = types; k->tr_a = S.tr_a; k->tr_t = S.tr_t; k->maxcols_t = S.maxcols_t; k->cluster = S.cluster;
   k->vec_bytes_a = ((pa.nslots() * sizeof(double) + 127) / 128) * 128;
+  k->pa_host = pa;
   const std::string cubin = spec_compile_source(S.src, &k->compile_seconds, &k->from_cache, only_if_cached);
   if (cubin.empty()) return nullptr;
   OB_CUDA(cudaSetDevice(c.device));
@@ -308,6 +316,53 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   p.partial = ws.partial.ensure((size_t)J * p.nslots);
   spec_launch(c, k.kt, k.smem_t_set, grid, 32 * (k.opt.wt + k.opt.np), g.smem, p, "phi_t_spec", k.cluster);
   launch_phi_t_reduce(c, p.partial, J, p.nslots, pr.slot_term.p, out);
+}
+
+bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* A, u64 C, double* out, u64 ldo) {
+  if (pl.N == 0 || C == 0) return true;
+  if (pl.cols->nload != pl.cols->ncol) return false;
+  if (k.mat_state == 0) {
+    k.mat_state = -1;
+    obs::SpecSource S = obs::generate_mat(k.pa_host, k.opt);
+    if (!S.ok) return false;
+    double sec = 0;
+    bool cached = false;
+    const std::string cubin = spec_compile_source(S.src, &sec, &cached, false);
+    OB_CUDA(cudaLibraryLoadData(&k.libm, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    OB_CUDA(cudaLibraryGetKernel(&k.km, k.libm, "phi_am_spec"));
+    k.nblk = S.nacc;
+    k.mat_state = 1;
+  }
+  if (k.mat_state != 1) return false;
+  const int TR = 128, MW = 4;
+  obs::SpecParams p{};
+  spec_fill(p, pl, TR);
+  obs::MatParams q{};
+  q.off_coef = 128;
+  q.off_phi = q.off_coef + 2 * 32 * 64 * 8;
+  p.off_tile = q.off_phi + MW * 32 * 40 * 8;
+  p.tile_doubles = (unsigned)((p.ncol + 1) * TR);
+  p.nstage = 1;
+  const size_t smem = p.off_tile + (size_t)p.tile_doubles * 8;
+  if (smem > c.smem_optin) return false;
+  const DevProgram& pr = *pl.prog;
+  const int nslots = (int)pr.host.nslots();
+  k.aperm.ensure((size_t)k.nblk * 32 * 64);
+  const int grid = std::max(1, std::min(p.ntiles, c.sms));
+  for (u64 c0 = 0; c0 < C; c0 += 64) {
+    const int nc = (int)std::min<u64>(64, C - c0);
+    launch_gather_coef_blocks(c, A, pr.host.K, c0, nc, pr.slot_term.p, nslots, k.nblk, k.aperm.p);
+    q.aperm = k.aperm.p; q.out = out + c0 * ldo; q.ldo = ldo; q.ncols = nc; q.nblocks = k.nblk;
+    if (smem > k.smem_m_set) {
+      OB_CUDA(cudaFuncSetAttribute((const void*)k.km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k.smem_m_set = smem;
+    }
+    void* args[] = {&p, &q};
+    const cudaError_t e = cudaLaunchKernel((const void*)k.km, dim3(grid), dim3(32 * (MW + 2)), args, smem, c.stream);
+    if (e != cudaSuccess) throw CudaError(std::string("phi_am_spec: ") + cudaGetErrorString(e));
+    c.launches++;
+  }
+  return true;
 }
 
 } // namespace obd

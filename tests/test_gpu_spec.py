@@ -213,3 +213,20 @@ print("multicast OK", info)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
                          cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
     assert res.returncode == 0 and "multicast OK" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("N,K,C", [(300, 60, 8), (1000, 200, 20), (4000, 500, 64), (777, 150, 70)])
+def test_multi_rhs_tensor_core_kernel(spec, oracle, N, K, C):
+    """prodmm_(mat) (linalg.cpp:527-557) as one dense contraction on the FP64 tensor cores (phi_am_spec, DMMA):
+    eight or more columns of a specialised table; plain and squared operators against the oracle."""
+    o = oracle_basis(oracle, N, K)
+    terms, rng = o["terms"], o["rng"]
+    A = np.asfortranarray(rng.normal(size=(K, C)))
+    n0 = spec.launch_count()
+    got = spec.prodmm(terms, A, o["bm"], o["bs"], o["kp"])
+    assert relerr(got, o["ob"].matmul(terms, A)) < MATVEC_TOL
+    assert spec.launch_count() - n0 <= 2 * ((C + 63) // 64)  # gather + one tensor-core launch per 64 columns, no column loop
+    omg, x, y, t2, _ = make_problem(spec, N, K)
+    obg = spec.outerbase(omg, x)
+    assert relerr(obg.sqmm(t2, np.abs(A)), o["ob"].sqmm(t2, np.abs(A))) < 1e-9
+    assert relerr(obg.matmul(t2, A[:, :3]), o["ob"].matmul(t2, A[:, :3])) < 1e-9  # fewer than 8 columns: vector kernels
