@@ -171,7 +171,7 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
  * The module is generated and compiled at first use.  Returns false when the tile does not fit (caller: column loop). */
 bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* A, u64 C, double* out, u64 ldo);
 /* coefficient blocks in emit order, columns of odd rows swizzled (ob_spec_scaffold.inc, phi_am_spec) */
-void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nblk, double* out);
+void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nrows, double* out);
 /* explicit Phi (N x K column-major, device), getm_ linalg.cpp:685-715 */
 void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo);
 /* sum of n per-CTA partials, fixed order -> out[0] */

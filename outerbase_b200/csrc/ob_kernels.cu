@@ -1099,17 +1099,17 @@ void launch_masked_add(Ctx& c, const double* a, const double* b, const unsigned 
 }
 
 __global__ void gather_coef_blocks_kernel(const double* __restrict__ A, unsigned long long K, unsigned long long col0, int ncols,
-                                         const int32_t* __restrict__ slot_term, int nslots, int nblk, double* __restrict__ out) {
+                                         const int32_t* __restrict__ slot_term, int nslots, int nrows, double* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x; /* one thread per (slot, column) */
-  if (idx >= nblk * 32 * 64) return;
+  if (idx >= nrows * 64) return;
   const int s = idx >> 6, c = idx & 63;
   double v = 0.0;
   if (s < nslots && c < ncols) { const int t = slot_term[s]; if (t >= 0) v = A[(unsigned long long)t + (col0 + c) * K]; }
   out[(size_t)s * 64 + (c ^ ((s & 1) << 3))] = v;
 }
-void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nblk, double* out) {
-  const int n = nblk * 32 * 64;
-  gather_coef_blocks_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(A, K, col0, ncols, slot_term, nslots, nblk, out);
+void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nrows, double* out) {
+  const int n = nrows * 64;
+  gather_coef_blocks_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(A, K, col0, ncols, slot_term, nslots, nrows, out);
   check_launch(c, "gather_coef_blocks_kernel");
 }
 

@@ -69,6 +69,8 @@ struct SpecOptions {
   int mc = 0;
   /* Phi^T: passes of a tile interleaved by the compiler (unroll factor of the pass loop) */
   int ut = 1;
+  /* multi-RHS kernel: compute warps (32 rows each) per tile and terms per block */
+  int mw = 8, kc = 16;
 };
 
 struct SpecSource {
@@ -253,12 +255,12 @@ inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cach
  * park Phi[row, term] of the block's emits in the warp's shared-memory block (OBS_M_EMIT), then ONE shared instance
  * of the tensor-core contraction runs (OBS_M_BLOCK).  The interpreter's running product and register stack are
  * plain variables (cu, s0..s8) that live across the cases.  Returns the emit count. */
-inline int emit_mat(Emitter& e, const Program& P, int TR) {
+inline int emit_mat(Emitter& e, const Program& P, int TR, int KC) {
   using namespace obt;
   int ia = 0;
   bool open = false;
-  auto begin_case = [&]() { if (!open) { e.f("case %d: {\n", ia / 32); open = true; } };
-  auto emitted = [&]() { if (++ia % 32 == 0) { e.f("} break;\n"); open = false; } };
+  auto begin_case = [&]() { if (!open) { e.f("case %d: {\n", ia / KC); open = true; } };
+  auto emitted = [&]() { if (++ia % KC == 0) { e.f("} break;\n"); open = false; } };
   auto fac = [&](uint32_t col) { char b[64]; std::snprintf(b, sizeof b, "ldv(tp + %uu)", (unsigned)(col * TR) * 8u); return std::string(b); };
   e.f("double cu = 1.0, s0 = 1.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0, s8 = 0.0;\n");
   e.f("_Pragma(\"unroll 1\") for (int blk = 0; blk < OBS_NBLK; ++blk) {\nswitch (blk) {\n");
@@ -268,22 +270,22 @@ inline int emit_mat(Emitter& e, const Program& P, int TR) {
     if (op == F_EMITZERO) continue;
     begin_case();
     if (op == F_LEAF) {
-      e.f("OBS_M_EMIT(%d, cu * %s);\n", ia % 32, fac(col).c_str());
+      e.f("OBS_M_EMIT(%d, cu * %s);\n", ia % KC, fac(col).c_str());
       emitted();
     } else if (op == F_DESC_CUR || op == F_DESC_STK) {
       if (op == F_DESC_STK) e.f("cu = s%u * %s;\n", d - 1, fac(col).c_str());
       else e.f("cu = cu * %s;\n", fac(col).c_str());
       if (fl & FLAG_SAVE) e.f("s%u = cu;\n", d);
-      if (fl & FLAG_EMIT) { e.f("OBS_M_EMIT(%d, cu);\n", ia % 32); emitted(); }
+      if (fl & FLAG_EMIT) { e.f("OBS_M_EMIT(%d, cu);\n", ia % KC); emitted(); }
     } else if (op == F_ROOT) {
-      e.f("OBS_M_EMIT(%d, s0);\n", ia % 32);
+      e.f("OBS_M_EMIT(%d, s0);\n", ia % KC);
       emitted();
     } else if (op == F_LOADCUR) {
       e.f("cu = s%u;\n", d);
     }
   }
   const int n = ia;
-  if (ia % 32) { begin_case(); while (ia % 32) { e.f("OBS_M_EMIT(%d, 0.0);\n", ia % 32); ++ia; } e.f("} break;\n"); open = false; }
+  if (ia % KC) { begin_case(); while (ia % KC) { e.f("OBS_M_EMIT(%d, 0.0);\n", ia % KC); ++ia; } e.f("} break;\n"); open = false; }
   if (open) e.f("} break;\n");
   e.f("default: break;\n}\nOBS_M_BLOCK()\n}\n");
   return n;
@@ -439,18 +441,20 @@ inline SpecSource generate_mat(const Program& pa, const SpecOptions& opt) {
   using namespace detail;
   SpecSource S;
   S.opt = opt;
-  S.tr_a = 128;
+  const int MW = opt.mw, KC = opt.kc;
+  S.tr_a = 32 * MW;
   if (!pa.fast_ok || pa.G != 1 || pa.tmem_cap || pa.K == 0) { S.why = "program does not match"; return S; }
+  if ((MW != 4 && MW != 8) || (KC != 16 && KC != 32)) { S.why = "unsupported multi-RHS geometry"; return S; }
   Emitter hdr, tab, body;
   hdr.f("#define OBS_PARAM_BYTES %d\n#define OBS_K %llu\n#define OBS_NP 1\n#define OBS_HAVE_M 1\n#define OBS_NCOLS_A %d\n", (int)sizeof(SpecParams),
         (unsigned long long)pa.K, (int)pa.cols.size());
   tab.f("__device__ const unsigned short obs_cols_a[] = {");
   for (size_t c = 0; c < pa.cols.size(); ++c) tab.f("%d,", (int)c);
   tab.f("0};\n");
-  const int n = emit_mat(body, pa, S.tr_a);
+  const int n = emit_mat(body, pa, S.tr_a, KC);
   if (n != (int)pa.slot_real[0]) { S.why = "emit count mismatch"; return S; }
-  S.nacc = (n + 31) / 32; /* coefficient blocks per pass */
-  hdr.f("#define OBS_NBLK %d\n", S.nacc);
+  S.nacc = (n + KC - 1) / KC; /* coefficient blocks per pass */
+  hdr.f("#define OBS_NBLK %d\n#define OBS_KC %d\n#define OBS_MW %d\n", S.nacc, KC, MW);
   std::string src = scaffold_text();
   replace_marker(src, "//@@TABLES@@", tab.s);
   replace_marker(src, "//@@BODY_M@@", body.s);

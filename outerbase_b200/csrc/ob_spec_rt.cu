@@ -147,10 +147,10 @@ struct SpecKernels {
 
 obs::SpecOptions spec_default_options() {
   obs::SpecOptions o;
-  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut -- tuning only */
-    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut};
+  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc -- tuning only */
+    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut, &o.mw, &o.kc};
     int i = 0;
-    for (const char* p = e; *p && i < 12; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (const char* p = e; *p && i < 14; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
   }
   return o;
 }
@@ -334,31 +334,31 @@ bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double*
     k.mat_state = 1;
   }
   if (k.mat_state != 1) return false;
-  const int TR = 128, MW = 4;
+  const int MW = k.opt.mw, KC = k.opt.kc, TR = 32 * MW;
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
   obs::MatParams q{};
   q.off_coef = 128;
-  q.off_phi = q.off_coef + 2 * 32 * 64 * 8;
-  p.off_tile = q.off_phi + MW * 32 * 40 * 8;
+  q.off_phi = q.off_coef + 2 * KC * 64 * 8;
+  p.off_tile = q.off_phi + MW * KC * 40 * 8;
   p.tile_doubles = (unsigned)((p.ncol + 1) * TR);
   p.nstage = 1;
   const size_t smem = p.off_tile + (size_t)p.tile_doubles * 8;
   if (smem > c.smem_optin) return false;
   const DevProgram& pr = *pl.prog;
   const int nslots = (int)pr.host.nslots();
-  k.aperm.ensure((size_t)k.nblk * 32 * 64);
+  k.aperm.ensure((size_t)k.nblk * KC * 64);
   const int grid = std::max(1, std::min(p.ntiles, c.sms));
   for (u64 c0 = 0; c0 < C; c0 += 64) {
     const int nc = (int)std::min<u64>(64, C - c0);
-    launch_gather_coef_blocks(c, A, pr.host.K, c0, nc, pr.slot_term.p, nslots, k.nblk, k.aperm.p);
+    launch_gather_coef_blocks(c, A, pr.host.K, c0, nc, pr.slot_term.p, nslots, k.nblk * KC, k.aperm.p);
     q.aperm = k.aperm.p; q.out = out + c0 * ldo; q.ldo = ldo; q.ncols = nc; q.nblocks = k.nblk;
     if (smem > k.smem_m_set) {
       OB_CUDA(cudaFuncSetAttribute((const void*)k.km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k.smem_m_set = smem;
     }
     void* args[] = {&p, &q};
-    const cudaError_t e = cudaLaunchKernel((const void*)k.km, dim3(grid), dim3(32 * (MW + 2)), args, smem, c.stream);
+    const cudaError_t e = cudaLaunchKernel((const void*)k.km, dim3(grid), dim3(32 * MW), args, smem, c.stream);
     if (e != cudaSuccess) throw CudaError(std::string("phi_am_spec: ") + cudaGetErrorString(e));
     c.launches++;
   }
