@@ -199,6 +199,8 @@ double measure_fp64_peak(Ctx& c);
  * T_k^(-l) (linalg.cpp:139-163); sq: the same for the squared matrices, basematsq_gradhyp = 2 G % B
  * (modandbase.cpp:588-590): C_j = 2 B_j % (G_j - G_0 % B_j) */
 void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, double* out, int sq = 0);
+/* out[i] = in[i]^2 */
+void launch_square(Ctx& c, const double* in, u64 n, double* out);
 /* out[n] = c * g[n] * w[n] */
 void launch_scaled_product(Ctx& c, double coef, const double* g, const double* w, u64 n, double* out);
 /* out[k] = a[k] + (mask[k] ? b[k] : 0) */

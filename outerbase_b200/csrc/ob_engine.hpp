@@ -46,6 +46,19 @@ struct OuterBase {
   u64 om_version = 0;
   std::vector<u64> knotptst, gest, hypmatch, hypst;
   DevBuf<double> x, basemat, basematge, scalemat, scale;
+  /* basematsq (modandbase.cpp:527-531), materialised at the first squared operator after a build: squaring the staged
+   * tile inside the Phi kernels instead made every squared product 3x slower than the plain one, and a BFGS
+   * evaluation runs 1 + 2H of them (diaghess, diaghessgradhyp) */
+  DevBuf<double> basematsq;
+  bool sq_valid = false;
+  const double* sq_matrix() {
+    if (!sq_valid) {
+      basematsq.ensure(ld * M);
+      obd::launch_square(ctx, basemat.p, ld * M, basematsq.p);
+      sq_valid = true;
+    }
+    return basematsq.p;
+  }
   DevBuf<double> knots_dev, rot_dev, rotg_dev;
   obd::Workspace ws;
   DevBuf<double> tmpK, tmpN, tmpN2, tmpP;
@@ -149,6 +162,7 @@ struct OuterBase {
                             dograd ? basematge.p : nullptr, scalemat.p, scale.p, dograd);
     ctx.sync(); /* host vectors above must outlive the async uploads */
     coltables.clear(); /* buffers may have moved */
+    sq_valid = false;
     om_version = om->version;
   }
 
@@ -332,8 +346,8 @@ struct OuterBase {
     std::vector<const double*> aux;
     for (const obt::ColRef& cr : P.cols) {
       if (!cr.aug) {
-        src.push_back(basemat.p + (knotptst[cr.dim] + cr.level) * ld);
-        ops.push_back(sq ? obd::COL_SQUARE : obd::COL_COPY);
+        src.push_back((sq ? sq_matrix() : basemat.p) + (knotptst[cr.dim] + cr.level) * ld);
+        ops.push_back(obd::COL_COPY);
       } else {
         if (h < 0 || hypmatch[h] != cr.dim || !dograd) throw std::logic_error("gradient column without a hyper-parameter");
         src.push_back(basematge.p + (gest[h] + cr.level) * ld);
@@ -349,7 +363,7 @@ struct OuterBase {
     e.ct->ncol = (int)src.size();
     src.insert(src.end(), aux.begin(), aux.end());
     e.ct->nload = (int)src.size();
-    e.ct->has_ops = sq != 0;
+    e.ct->has_ops = !aux.empty();
     e.ct->load_src.upload(src, ctx.stream);
     e.ct->col_op.upload(ops, ctx.stream);
     ctx.sync();
@@ -409,11 +423,11 @@ struct OuterBase {
       for (size_t c = 0; c < nc; ++c) {
         const obt::ColRef& cr = P.cols[c];
         const bool mine = cr.dim == l;
-        e->gsrc_t_host[l * nc + c] = mine ? tmpC.p + (cr.level - 1) * ld : basemat.p + (knotptst[cr.dim] + cr.level) * ld;
-        e->gops_t_host[l * nc + c] = (sq && !mine) ? obd::COL_SQUARE : obd::COL_COPY;
+        e->gsrc_t_host[l * nc + c] = mine ? tmpC.p + (cr.level - 1) * ld : (sq ? sq_matrix() : basemat.p) + (knotptst[cr.dim] + cr.level) * ld;
+        e->gops_t_host[l * nc + c] = obd::COL_COPY;
       }
       obd::ColTable& ct = *e->gtab_t[l];
-      ct.ncol = ct.nload = (int)nc; ct.has_ops = sq != 0;
+      ct.ncol = ct.nload = (int)nc; ct.has_ops = false;
       ct.load_src.upload(e->gsrc_t_host.data() + l * nc, nc, ctx.stream);
       ct.col_op.upload(e->gops_t_host.data() + l * nc, nc, ctx.stream);
     }

@@ -1077,6 +1077,17 @@ void launch_gradcols(Ctx& c, const double* B, const double* G, u64 ld, u64 L, do
   gradcols_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, c.stream>>>(B, G, ld, L, out, sq);
   check_launch(c, "gradcols_kernel");
 }
+__global__ void square_kernel(const double* __restrict__ in, unsigned long long n, double* __restrict__ out) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const double x = in[i];
+    out[i] = x * x;
+  }
+}
+void launch_square(Ctx& c, const double* in, u64 n, double* out) {
+  if (n == 0) return;
+  square_kernel<<<c.sms * 16, 256, 0, c.stream>>>(in, n, out);
+  check_launch(c, "square_kernel");
+}
 __global__ void scaled_product_kernel(double coef, const double* __restrict__ g, const double* __restrict__ w, unsigned long long n,
                                       double* __restrict__ out) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

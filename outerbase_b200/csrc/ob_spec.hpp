@@ -43,7 +43,7 @@ struct SpecParams {
   double sd;
   unsigned long long N;
   int ncol, has_ops, sq, mode, ntiles, nstage, nslots;
-  unsigned off_tile, tile_doubles, off_vec;
+  unsigned off_tile, tile_doubles, off_vec, off_flags;
 };
 
 /* mirrored by `struct MatParams` in ob_spec_scaffold.inc (phi_am_spec) */

@@ -226,8 +226,8 @@ static void spec_launch(Ctx& c, cudaKernel_t kern, size_t& smem_set, int grid, i
 struct SpecGeom { int nstage = 0; unsigned off_vec = 0, off_tile = 0, tile_doubles = 0; size_t smem = 0; };
 static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t vec_bytes, int want_stages) {
   SpecGeom g;
-  g.off_vec = 128;
-  g.off_tile = (unsigned)(128 + vec_bytes);
+  g.off_vec = 128 + 256; /* 16 mbarriers | 256 square flags | ... */
+  g.off_tile = (unsigned)(g.off_vec + vec_bytes);
   g.tile_doubles = (unsigned)((ncol + nextra) * TR);
   const size_t tile_bytes = (size_t)g.tile_doubles * 8;
   const size_t room = c.smem_optin > g.off_tile ? c.smem_optin - g.off_tile : 0;
@@ -252,6 +252,7 @@ obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, 
 }
 
 bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol) {
+  if (ncol + 2 > 256) return false; /* one square flag per tile column in a 256-byte block */
   /* a consumer group must never be a whole round of stages ahead of the producer (mbarrier parity
    * would alias): tiles in work at once <= stages */
   return spec_geometry(c, ncol, 1, k.tr_a, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (k.opt.qa * k.opt.tga + k.opt.np)), 8).nstage >= k.opt.tga &&
@@ -267,7 +268,7 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
   /* the coefficient copy doubles as the scratch of the final residual reduction (one double per thread) */
   const SpecGeom g = spec_geometry(c, p.ncol, 1, TR, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (warps + k.opt.np)), k.opt.tga + 2);
   if (g.nstage < k.opt.tga) throw std::logic_error("specialised Phi a does not fit in shared memory");
-  p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles;
+  p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles; p.off_flags = 128;
   p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
   const int grid = std::max(1, std::min(p.ntiles, c.sms));
   if (a.mode == PHI_UPDATE || a.mode == PHI_DOT) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
@@ -288,7 +289,7 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   spec_fill(p, pl, TR);
   const SpecGeom g = spec_geometry(c, k.maxcols_t, 2, TR, 0, 4);
   if (g.nstage < 1) throw std::logic_error("specialised Phi^T does not fit in shared memory");
-  p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles;
+  p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles; p.off_flags = 128;
   int jmax = c.sms / k.types;
   if (k.cluster > 1) { /* clusters that can be resident at once: a second, partial wave would double the time */
     if (k.max_clusters == 0 || g.smem > k.smem_t_set) {
@@ -338,7 +339,8 @@ bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double*
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
   obs::MatParams q{};
-  q.off_coef = 128;
+  p.off_flags = 128;
+  q.off_coef = 128 + 256;
   q.off_phi = q.off_coef + 2 * KC * 64 * 8;
   p.off_tile = q.off_phi + MW * KC * 40 * 8;
   p.tile_doubles = (unsigned)((p.ncol + 1) * TR);
