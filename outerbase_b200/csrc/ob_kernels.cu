@@ -692,6 +692,118 @@ __global__ void __launch_bounds__(256) basis_build_kernel(const BuildKParams p) 
   }
 }
 
+/* Tensor-core variant of the basis build: the m x m (+ gradient) contractions of buildob (modandbase.cpp:285-327) as
+ * FP64 DMMAs (mma.sync.m8n8k4.f64).  64 rows per CTA, 8 warps = 8 row tiles; warp w contracts rows 8w..8w+7 against
+ * all NT column tiles of the rotation blocks: per k-step 1 (+nh) A fragments from the covariance tile in shared
+ * memory and (1+nh) NT B fragments from the rotation blocks, 1 + 2 nh DMMAs per column tile, with Rt = covg.rot +
+ * cov.rotg accumulated in ONE tile.  Strides 72 / 44|76 doubles keep every fragment load at the minimum two
+ * shared-memory wavefronts.  The existing FMA kernel stays for m > 72. */
+__device__ __forceinline__ void dmma_f64(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int NT>
+__global__ void __launch_bounds__(256) basis_build_mma_kernel(const BuildKParams p) {
+  constexpr int ROWS = 64, CS = ROWS + 8, RS = NT * 8 + 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const int m = p.m, nh = p.dograd ? p.nh : 0, mk = (m + 3) & ~3;
+  double* rotT = sm;                                    /* (1+nh) * mk * RS : element (p, j), zero padded */
+  double* Cs = rotT + (size_t)(1 + nh) * mk * RS;       /* (1+nh) * mk * CS : element (p, row), zero padded */
+  double* kt = Cs + (size_t)(1 + nh) * mk * CS;         /* 2*m knot transforms */
+  double* xt = kt + 2 * m;                              /* 2*ROWS row transforms */
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, k4 = lane & 3;
+  const int ntiles = (m + 7) / 8;
+
+  /* once per CTA: rotation blocks, knot transforms, zero padding (persistent CTAs walk the row tiles) */
+  for (int idx = tid; idx < (1 + nh) * mk * RS; idx += 256) rotT[idx] = 0.0;
+  for (int idx = tid; idx < (1 + nh) * mk * CS; idx += 256) Cs[idx] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += 256) {
+    const int pp = idx % m, j = idx / m; /* column-major source: element (pp, j) */
+    rotT[(size_t)pp * RS + j] = p.rot[pp + (unsigned long long)j * p.rot_ld];
+    if (nh > 0) rotT[(size_t)(mk + pp) * RS + j] = p.rotg0[pp + (unsigned long long)j * p.rot_ld];
+    if (nh > 1) rotT[(size_t)(2 * mk + pp) * RS + j] = p.rotg1[pp + (unsigned long long)j * p.rot_ld];
+  }
+  for (int idx = tid; idx < m; idx += 256) {
+    const CovPt c = cov_transform_dev(p.kind, p.h0, p.h1, p.knots[idx]);
+    kt[idx] = c.t; kt[m + idx] = c.s;
+  }
+  const unsigned long long nrt = (p.ld + ROWS - 1) / ROWS;
+  for (unsigned long long rt = blockIdx.x; rt < nrt; rt += gridDim.x) {
+    const unsigned long long row0 = rt * ROWS;
+    __syncthreads(); /* previous tile's fragments are consumed; knot transforms are visible */
+    for (int idx = tid; idx < ROWS; idx += 256) {
+      const unsigned long long row = row0 + idx;
+      CovPt c{0.0, 0.0};
+      if (row < p.N) c = cov_transform_dev(p.kind, p.h0, p.h1, p.x[row]);
+      xt[idx] = c.t; xt[ROWS + idx] = c.s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < m * ROWS; idx += 256) {
+      const int r = idx % ROWS, pp = idx / ROWS;
+      const CovPt a{xt[r], xt[ROWS + r]}, b{kt[pp], kt[m + pp]};
+      double v, g0 = 0, g1 = 0;
+      if (nh > 0) cov_pair_dev<true>(p.kind, p.h1, a, b, v, g0, g1);
+      else cov_pair_dev<false>(p.kind, p.h1, a, b, v, g0, g1);
+      Cs[(size_t)pp * CS + r] = v;
+      if (nh > 0) Cs[(size_t)(mk + pp) * CS + r] = g0;
+      if (nh > 1) Cs[(size_t)(2 * mk + pp) * CS + r] = g1;
+    }
+    __syncthreads();
+
+    double acc[3][NT][2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int jt = 0; jt < NT; ++jt) acc[q][jt][0] = acc[q][jt][1] = 0.0;
+    for (int kk = 0; kk < mk / 4; ++kk) {
+      const int pp = kk * 4 + k4;
+      const double a0 = Cs[(size_t)pp * CS + warp * 8 + g];
+      const double a1 = nh > 0 ? Cs[(size_t)(mk + pp) * CS + warp * 8 + g] : 0.0;
+      const double a2 = nh > 1 ? Cs[(size_t)(2 * mk + pp) * CS + warp * 8 + g] : 0.0;
+#pragma unroll
+      for (int jt = 0; jt < NT; ++jt) {
+        if (jt < ntiles) {
+          const double b0 = rotT[(size_t)pp * RS + jt * 8 + g];
+          dmma_f64(acc[0][jt][0], acc[0][jt][1], a0, b0);
+          if (nh > 0) {
+            const double b1 = rotT[(size_t)(mk + pp) * RS + jt * 8 + g];
+            dmma_f64(acc[1][jt][0], acc[1][jt][1], a1, b0);
+            dmma_f64(acc[1][jt][0], acc[1][jt][1], a0, b1);
+          }
+          if (nh > 1) {
+            const double b2 = rotT[(size_t)(2 * mk + pp) * RS + jt * 8 + g];
+            dmma_f64(acc[2][jt][0], acc[2][jt][1], a2, b0);
+            dmma_f64(acc[2][jt][0], acc[2][jt][1], a0, b2);
+          }
+        }
+      }
+    }
+    /* column 0 of the projected basis = the per-row scale P_l[:,0] (modandbase.cpp:297,572): C fragment element
+     * (g, 0) lives in the first lane of every 4-lane group */
+    const double p0 = __shfl_sync(0xffffffffu, acc[0][0][0], lane & ~3);
+    const unsigned long long row = row0 + warp * 8 + g;
+    const bool live = row < p.N;
+    if (row < p.ld) {
+      if (k4 == 0) p.scalecol[row] = live ? p0 : 0.0;
+#pragma unroll
+      for (int jt = 0; jt < NT; ++jt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = jt * 8 + 2 * k4 + e;
+          if (j < m) {
+            double v = 0.0;
+            if (live) v = (j == 0) ? 1.0 : acc[0][jt][e] / p0;
+            p.bm[row + (unsigned long long)j * p.ld] = v;
+            if (nh > 0) p.bg0[row + (unsigned long long)j * p.ld] = live ? acc[1][jt][e] / p0 : 0.0;
+            if (nh > 1) p.bg1[row + (unsigned long long)j * p.ld] = live ? acc[2][jt][e] / p0 : 0.0;
+          }
+        }
+    }
+  }
+}
+
 /* basescale = prod_l P_l[:,0], multiplied in dimension order (modandbase.cpp:573) */
 __global__ void basescale_kernel(const double* scalemat, unsigned long long ld, int d, unsigned long long N, double* scale) {
   const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1168,7 +1280,18 @@ void launch_basis_build(Ctx& c, const std::vector<BuildDims>& dims, const double
     auto need = [&](int rows) {
       return ((size_t)(1 + nh) * D.m * p.mp + (size_t)(1 + nh) * D.m * rows + 2 * D.m + 2 * rows) * sizeof(double);
     };
-    if (need(64) <= c.smem_optin) {
+    const int mk = (D.m + 3) & ~3;
+    auto need_mma = [&](int nt) {
+      return ((size_t)(1 + nh) * mk * (nt * 8 + 4) + (size_t)(1 + nh) * mk * 72 + 2 * D.m + 2 * 64) * sizeof(double);
+    };
+    static const bool use_mma = !(getenv("OB_BUILD") && std::string(getenv("OB_BUILD")) == "fma");
+    if (use_mma && D.m <= 40 && need_mma(5) <= c.smem_optin) {
+      set_smem(basis_build_mma_kernel<5>, need_mma(5));
+      basis_build_mma_kernel<5><<<(unsigned)std::min<u64>((ld + 63) / 64, (u64)c.sms * 2), 256, need_mma(5), c.stream>>>(p);
+    } else if (use_mma && D.m <= 72 && need_mma(9) <= c.smem_optin) {
+      set_smem(basis_build_mma_kernel<9>, need_mma(9));
+      basis_build_mma_kernel<9><<<(unsigned)std::min<u64>((ld + 63) / 64, (u64)c.sms), 256, need_mma(9), c.stream>>>(p);
+    } else if (need(64) <= c.smem_optin) {
       set_smem(basis_build_kernel<64>, need(64));
       basis_build_kernel<64><<<(unsigned)((ld + 63) / 64), 256, need(64), c.stream>>>(p);
     } else if (need(32) <= c.smem_optin) {
