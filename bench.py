@@ -255,9 +255,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = lib.launch_count()
     e0.record(stream)
+    t_issue = time.perf_counter()
     for s in range(args.steps):
         step_dev(evs[s])
     e1.record(stream)
+    t_issue = (time.perf_counter() - t_issue) / args.steps * 1e3  # host time to ISSUE one step (launch-bound check)
     barrier()
     launches = lib.launch_count() - n0
     ms = e0.elapsed_time(e1)
@@ -268,6 +270,35 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, t_a, t_t = [float(v) for v in tms.cpu()]
     value = 2 * args.steps / (ms * 1e-3)
+
+    # ---- the cross-GPU sum on its own: K doubles, back to back (ranks in lockstep), both implementations
+    allreduce = None
+    if world > 1:
+        allreduce = {}
+        buf = torch.zeros(K_TERMS, dtype=torch.float64, device=dev)
+        for name, p2p in (("p2p_us", 1), ("nccl_us", 0)):
+            lib.set_option("p2p", p2p)
+            for _ in range(20):
+                lib.allreduce_dev(buf.data_ptr(), K_TERMS)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(200):
+                lib.allreduce_dev(buf.data_ptr(), K_TERMS)
+            a1.record(stream)
+            barrier()
+            allreduce[name] = a0.elapsed_time(a1) / 200 * 1e3
+            for _ in range(5):
+                ob.tmm_dev(r_d.data_ptr(), g_d.data_ptr())
+            barrier()
+            a0.record(stream)
+            for _ in range(100):
+                ob.tmm_dev(r_d.data_ptr(), g_d.data_ptr())
+            a1.record(stream)
+            barrier()
+            allreduce["phi_t_" + name] = a0.elapsed_time(a1) / 100 * 1e3
+        lib.set_option("p2p", 1)
+        allreduce["note"] = "K doubles, 200 back-to-back calls on the library stream; p2p falls back to NCCL when peer memory is not mapped"
 
     # ---- e2e: the reference-facing calls outerbase::mm / outerbase::tmm with HOST buffers, every call
     # copying its inputs in and its result out (pinned host memory on both sides, as the contract asks)
@@ -353,7 +384,7 @@ def main():
                     "traffic_source": traffic_src,
                     "peak_source": "DFMA micro-benchmark run in this process (nominal 37.2 TFLOP/s at 1965 MHz)",
                     "algorithmic_flop_per_launch": flop, "W": W, "Lcols": Lcols,
-                    "ms_phi_a": t_a, "ms_phi_t": t_t,
+                    "ms_phi_a": t_a, "ms_phi_t": t_t, "host_issue_ms_per_step": t_issue,
                     "hbm": {"achieved_gbs": bytes_alg / (t_dom * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                             "algorithmic_bytes_per_launch": bytes_alg}}
         line = {
@@ -366,7 +397,7 @@ def main():
                                    f"{spec_compile_s:.1f} s, 0 = disk-cache hit)") if args.spec == "1" else "interpreter",
                        "l2": f"inputs exceed L2: {nmax * 8 * (Lcols + 2) / 1e6:.0f} MB of basis columns per pass vs 126 MB"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk, "optcg": optcg,
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk, "optcg": optcg, "allreduce": allreduce,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -61,6 +61,12 @@ int ob_ctx_stream(ob_ctx* ctx, void** stream_out);
 int ob_comm_get_unique_id(void* id128);
 int ob_ctx_comm_init(ob_ctx* ctx, int nranks, int rank, const void* id128);
 int ob_ctx_comm_info(ob_ctx* ctx, int* nranks, int* rank);
+/* Sum buf_dev[0..n) over the ranks of the communicator, in place, on ctx's stream (not synchronised): the
+ * cross-GPU form of the reference's `#pragma omp critical: out += out_` (src/linalg.cpp:334-335, 438-442, 616-617).
+ * Every Phi^T-type call above does this itself; exposed for callers that keep their own row-sharded sums.
+ * Up to 65536 doubles travel through the one-shot peer-memory kernel (option "p2p", default 1 when the ranks can
+ * map each other's memory), larger payloads through ncclAllReduce.  All ranks must call it in the same order. */
+int ob_ctx_allreduce_dev(ob_ctx* ctx, double* buf_dev, uint64_t n);
 /* measured FP64 FMA peak of this GPU (TFLOP/s): the roofline denominator bench.py quotes. */
 int ob_ctx_fp64_peak(ob_ctx* ctx, double* tflops);
 /* test hook: number of CUDA kernels this context has launched so far. */

@@ -69,6 +69,7 @@ int orc_ctx_stream(orc_ctx*, void** s) { *s = nullptr; return ORC_OK; }
 int orc_comm_get_unique_id(void* id) { std::memset(id, 0, 128); return ORC_OK; }
 int orc_ctx_comm_init(orc_ctx*, int, int, const void*) { g_err = "oracle is single-rank"; return ORC_ERR_STATE; }
 int orc_ctx_comm_info(orc_ctx*, int* n, int* r) { *n = 1; *r = 0; return ORC_OK; }
+int orc_ctx_allreduce_dev(orc_ctx*, double*, uint64_t) { return ORC_OK; } /* one rank: the sum over ranks is the input */
 int orc_ctx_fp64_peak(orc_ctx*, double* t) { *t = 0; return ORC_OK; }
 int orc_ctx_launch_count(orc_ctx*, uint64_t* c) { *c = 0; return ORC_OK; }
 /* kernel specialisation is a property of the CUDA product; the oracle accepts and ignores the requests */

@@ -125,6 +125,10 @@ class Library:
         buf = C.create_string_buffer(uid, 128)
         self.call("ctx_comm_init", self.ctx, C.c_int(nranks), C.c_int(rank), buf)
 
+    def allreduce_dev(self, buf_ptr: int, n: int):
+        """In-place sum over ranks of n doubles at a device pointer, on the library's stream (not synchronised)."""
+        self.call("ctx_allreduce_dev", self.ctx, C.c_void_p(buf_ptr), C.c_uint64(n))
+
     def comm_info(self):
         n, r = C.c_int(), C.c_int()
         self.call("ctx_comm_info", self.ctx, C.byref(n), C.byref(r))

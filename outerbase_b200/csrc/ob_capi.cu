@@ -63,9 +63,13 @@ int ob_ctx_comm_init(ob_ctx* ctx, int nranks, int rank, const void* id128) {
   const int rc = api.CommInitRank(&comm, nranks, uid, rank);
   if (rc != 0) throw obd::NcclError(std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
   ctx->c.comm = comm; ctx->c.nranks = nranks; ctx->c.rank = rank;
+  ctx->c.p2p_init();
   OB_CATCH
 }
 int ob_ctx_comm_info(ob_ctx* ctx, int* nranks, int* rank) { OB_TRY need(ctx, "ctx"); *nranks = ctx->c.nranks; *rank = ctx->c.rank; OB_CATCH }
+int ob_ctx_allreduce_dev(ob_ctx* ctx, double* buf_dev, uint64_t n) {
+  OB_TRY need(ctx, "ctx"); if (n) need(buf_dev, "buf_dev"); ctx->c.allreduce_sum(buf_dev, n); OB_CATCH
+}
 int ob_ctx_fp64_peak(ob_ctx* ctx, double* tflops) { OB_TRY need(ctx, "ctx"); *tflops = obd::measure_fp64_peak(ctx->c); OB_CATCH }
 int ob_ctx_launch_count(ob_ctx* ctx, uint64_t* count) { OB_TRY need(ctx, "ctx"); *count = ctx->c.launches; OB_CATCH }
 
@@ -247,6 +251,7 @@ int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value) {
     if (value != 0 && value != 1 && value != 2) throw std::invalid_argument("spec must be 0, 1 or 2");
     ctx->c.spec_mode = (int)value;
   } else if (n == "spec_work") ctx->c.spec_work = value;
+  else if (n == "p2p") ctx->c.p2p.enabled = value != 0; /* same value on every rank */
   else throw std::invalid_argument("unknown option " + n);
   OB_CATCH
 }

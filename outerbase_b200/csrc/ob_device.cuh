@@ -41,6 +41,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUid*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   static NcclApi& get();
@@ -55,6 +56,21 @@ struct Ctx {
   void* comm = nullptr;
   int nranks = 1, rank = 0;
   double* pinned = nullptr; /* small pinned scratch for scalar read-back */
+  /* one-shot allreduce over NVLink peer memory (p2p_allreduce_kernel): every rank stores its K-vector straight into
+   * a slot of every peer's buffer and adds the slots it received in rank order.  Buffers are exchanged as CUDA IPC
+   * handles over the NCCL communicator at comm_init; NCCL stays the path for payloads above kCap doubles and when
+   * peer access is not available (p2p.G == 0). */
+  struct P2P {
+    static constexpr int kMaxRanks = 8;
+    static constexpr size_t kCap = 65536;      /* elements (16 bytes each: value + tags) per slot */
+    static constexpr int kThreads = 256;
+    int G = 0;
+    bool enabled = true;                       /* option "p2p": 0 sends everything through NCCL */
+    void* local = nullptr;                     /* slots [parity 2][rank G][kCap] */
+    void* peer[kMaxRanks] = {};                /* the same block of every rank, peer[rank] == local */
+    unsigned seq = 0;                          /* tag of the current call (never 0) */
+    unsigned long long timeout_ns = 120ull * 1000000000ull;
+  } p2p;
   /* terms-specialised kernels (ob_spec.hpp): 0 never, 1 at first use, 2 once a table has proven hot
    * (spec_work row-terms processed by the interpreter kernels) or its module is in the disk cache */
   int spec_mode = 2;
@@ -63,6 +79,25 @@ struct Ctx {
   ~Ctx();
   void sync() { OB_CUDA(cudaStreamSynchronize(stream)); }
   void allreduce_sum(double* buf_dev, size_t n);
+  bool p2p_ok(size_t n) const;
+  /* Fusion of a Phi^T product with the allreduce that follows it: fuse_allreduce(n) before the product asks the next
+   * launch_phi_t_reduce to combine the ranks in the same launch; allreduce_after(out, n) afterwards does the plain
+   * allreduce when the product did not end in that kernel (rows == 0, brute-force kernels). */
+  size_t fuse_n = 0;
+  bool fused = false;
+  void fuse_allreduce(size_t n) { fused = false; fuse_n = p2p_ok(n) ? n : 0; }
+  void allreduce_after(double* buf_dev, size_t n) {
+    fuse_n = 0;
+    if (!fused) allreduce_sum(buf_dev, n);
+    fused = false;
+  }
+  struct FuseScope { /* exception-safe request: a product that throws must not leave the request armed */
+    Ctx& c;
+    FuseScope(Ctx& c_, size_t n) : c(c_) { c.fuse_allreduce(n); }
+    ~FuseScope() { c.fuse_n = 0; }
+  };
+  void p2p_init();  /* after the NCCL communicator exists; leaves p2p.G == 0 when peer memory cannot be mapped */
+  void p2p_release();
 };
 
 /* device buffer, grows on demand, never shrinks */

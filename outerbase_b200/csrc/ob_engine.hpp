@@ -383,8 +383,10 @@ struct OuterBase {
     phi_a(terms, K, sq, a, nullptr);
   }
   void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true, u64 w_rows = ~(u64)0) {
+    if (!reduce_ranks) { phi_t(terms, K, sq, w_dev, out_dev, w_rows); return; }
+    obd::Ctx::FuseScope fuse(ctx, K); /* cross-CTA and cross-rank reductions in one launch when peer memory is mapped */
     phi_t(terms, K, sq, w_dev, out_dev, w_rows);
-    if (reduce_ranks) ctx.allreduce_sum(out_dev, K);
+    ctx.allreduce_after(out_dev, K);
   }
   /* prodmmge_: outge column h = augmented-program product (ob_terms.hpp) */
   void mm_ge_dev(const u64* terms, u64 K, int sq, const double* a_dev, double* out_dev, double* outge_dev, u64 ldo) {
@@ -809,8 +811,11 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     a.a = kbuf.p; a.w = w.p; a.sd = obssd; a.mode = obd::PHI_HESS;
     ob.phi_a(terms.data(), K, 0, a, nullptr);
     red.ensure(K);
-    ob.phi_t(terms.data(), K, 0, w.p, red.p);
-    ctx.allreduce_sum(red.p, K);
+    {
+      obd::Ctx::FuseScope fuse(ctx, K);
+      ob.phi_t(terms.data(), K, 0, w.p, red.p);
+      ctx.allreduce_after(red.p, K);
+    }
     std::vector<double> o(K);
     ob.d2h(o.data(), red.p, K);
     return o;

@@ -874,6 +874,7 @@ NcclApi& NcclApi::get() {
       api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
       api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
       api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+      api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
       api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
     }
@@ -902,13 +903,165 @@ Ctx::Ctx(int dev) : device(dev) {
 }
 
 Ctx::~Ctx() {
+  p2p_release();
   if (comm && NcclApi::get().CommDestroy) NcclApi::get().CommDestroy(comm);
   if (pinned) cudaFreeHost(pinned);
   if (stream) cudaStreamDestroy(stream);
 }
 
+/* ---- one-shot allreduce over NVLink peer memory (the reference's `omp critical: out += out_`,
+ * linalg.cpp:334-335, across GPUs).  A K-vector is 16 KB: the exchange is pure latency, so instead of a ring every
+ * rank stores its values directly into slot [parity][rank] of EVERY peer's buffer (NVSwitch gives each pair full
+ * bandwidth) and adds the G slots it receives in rank order -- all ranks add the same numbers in the same order, so the
+ * result is bit-identical everywhere, as the replicated CG algebra needs.
+ * Synchronisation is per ELEMENT and carried by the data itself: a double travels as two 8-byte words
+ * {low half, tag}, {high half, tag} (8-byte stores are single-copy atomic over NVLink), tag = the call's sequence
+ * number; the receiver polls an element until both tags match.  No flags, no system-scope fences (a
+ * `fence.sys` behind remote stores costs a round trip per CTA: a first version with flags measured 26 us against
+ * NCCL's 13 us at 2 ranks), no CTA barriers.  Slots alternate by the parity of the sequence number: a rank can only be
+ * one call ahead of a peer (call s+1 completes only with every rank's s+1 data, sent after that rank finished call s),
+ * so nobody overwrites an element that is still being polled. */
+struct P2PArgs {
+  uint4* slots[Ctx::P2P::kMaxRanks];
+  int G, rank;
+  unsigned seq;
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void p2p_push(const P2PArgs& a, size_t at, double v) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  const unsigned lo = (unsigned)u, hi = (unsigned)(u >> 32);
+#pragma unroll 1
+  for (int r = 0; r < a.G; ++r) { /* first stores spread over the peers */
+    uint4* q = a.slots[(a.rank + r) % a.G] + at;
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q), "r"(lo), "r"(a.seq), "r"(hi), "r"(a.seq) : "memory");
+  }
+}
+
+__device__ __forceinline__ double p2p_poll(const P2PArgs& a, const uint4* q) {
+  unsigned lo, f0, hi, f1;
+  unsigned long long t0 = 0, spins = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(q) : "memory");
+    if (f0 == a.seq && f1 == a.seq) break;
+    if ((++spins & 1023) == 0) { /* a peer that died must not hang this GPU for ever */
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > a.timeout_ns) __trap();
+    }
+  }
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+
+/* FUSED: the front end is phi_t_reduce_kernel (per-CTA partial sums of the Phi^T kernels added in CTA order, slot ->
+ * term scatter) and its results go straight to the peers: Phi^T r's cross-CTA and cross-GPU reductions are ONE launch.
+ * Ranks may mix the two variants within one call (a rank without rows has nothing to reduce). */
+template <bool FUSED>
+__global__ void __launch_bounds__(Ctx::P2P::kThreads) p2p_allreduce_kernel(const P2PArgs a, double* __restrict__ buf, int n,
+                                                                            const double* __restrict__ partial, int nblocks,
+                                                                            int nslots, const int32_t* __restrict__ slot_term) {
+  constexpr size_t cap = Ctx::P2P::kCap;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t par = (size_t)(a.seq & 1) * a.G;
+  const size_t my_slot = (par + a.rank) * cap;
+  if (FUSED) {
+    for (int i = gtid; i < nslots; i += gridDim.x * blockDim.x) {
+      const int t = slot_term[i];
+      if (t < 0) continue;
+      double v = 0.0;
+      for (int b = 0; b < nblocks; ++b) v += partial[(size_t)b * nslots + i];
+      p2p_push(a, my_slot + t, v);
+    }
+  } else if (gtid < n) {
+    p2p_push(a, my_slot + gtid, buf[gtid]);
+  }
+  if (gtid < n) {
+    const uint4* mine = a.slots[a.rank] + par * cap + gtid;
+    double s = p2p_poll(a, mine);
+    for (int r = 1; r < a.G; ++r) s += p2p_poll(a, mine + (size_t)r * cap);
+    buf[gtid] = s;
+  }
+}
+
+void Ctx::p2p_release() {
+  for (int r = 0; r < P2P::kMaxRanks; ++r)
+    if (p2p.peer[r] && p2p.peer[r] != p2p.local) cudaIpcCloseMemHandle(p2p.peer[r]);
+  if (p2p.local) cudaFree(p2p.local);
+  const bool en = p2p.enabled;
+  p2p = P2P();
+  p2p.enabled = en;
+}
+
+void Ctx::p2p_init() {
+  NcclApi& api = NcclApi::get();
+  if (const char* e = getenv("OB_P2P")) if (std::string(e) == "0") return;
+  if (nranks < 2 || nranks > P2P::kMaxRanks || !comm || !api.AllGather) return;
+  if (const char* e = getenv("OB_P2P_TIMEOUT_S")) p2p.timeout_ns = (unsigned long long)(atof(e) * 1e9);
+  const size_t bytes = 2 * (size_t)nranks * P2P::kCap * sizeof(uint4);
+  OB_CUDA(cudaMalloc(&p2p.local, bytes));
+  OB_CUDA(cudaMemsetAsync(p2p.local, 0, bytes, stream));
+  /* exchange the IPC handles (and whether this rank could export one) over the communicator */
+  struct Rec { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+  static_assert(sizeof(Rec) == 128, "one record per rank");
+  Rec mine{};
+  mine.ok = cudaIpcGetMemHandle(&mine.h, p2p.local) == cudaSuccess ? 1 : 0;
+  if (!mine.ok) cudaGetLastError();
+  DevBuf<Rec> all;
+  all.ensure((size_t)nranks);
+  OB_CUDA(cudaMemcpyAsync(all.p + rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice, stream));
+  int rc = api.AllGather(all.p + rank, all.p, sizeof(Rec), /*ncclChar*/ 0, comm, stream);
+  if (rc != 0) throw NcclError(std::string("ncclAllGather: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+  std::vector<Rec> recs((size_t)nranks);
+  OB_CUDA(cudaMemcpyAsync(recs.data(), all.p, sizeof(Rec) * nranks, cudaMemcpyDeviceToHost, stream));
+  sync();
+  int ok = 1;
+  for (int r = 0; r < nranks; ++r) ok &= recs[r].ok;
+  for (int r = 0; r < nranks && ok; ++r) {
+    if (r == rank) { p2p.peer[r] = p2p.local; continue; }
+    if (cudaIpcOpenMemHandle(&p2p.peer[r], recs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      p2p.peer[r] = nullptr;
+      ok = 0;
+    }
+  }
+  /* all ranks must take the same path: agree on the outcome (sum of ok flags == nranks) */
+  double* agree = reinterpret_cast<double*>(all.p);
+  const double okd = ok;
+  OB_CUDA(cudaMemcpyAsync(agree, &okd, sizeof(double), cudaMemcpyHostToDevice, stream));
+  rc = api.AllReduce(agree, agree, 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
+  if (rc != 0) throw NcclError(std::string("ncclAllReduce: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+  double total = 0;
+  OB_CUDA(cudaMemcpyAsync(&total, agree, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  sync();
+  const bool verbose = getenv("OB_VERBOSE") != nullptr;
+  if ((int)total != nranks) {
+    if (verbose) fprintf(stderr, "[outerbase_b200] rank %d: peer memory not available (%d of %d ranks), allreduce stays on NCCL\n", rank, (int)total, nranks);
+    p2p_release();
+    return;
+  }
+  p2p.G = nranks;
+  if (verbose) fprintf(stderr, "[outerbase_b200] rank %d: one-shot allreduce over peer memory, %d ranks\n", rank, nranks);
+}
+
+static void p2p_launch(Ctx& c, double* buf, size_t n, const double* partial, int nblocks, int nslots, const int32_t* slot_term) {
+  P2PArgs a{};
+  for (int r = 0; r < c.p2p.G; ++r) a.slots[r] = reinterpret_cast<uint4*>(c.p2p.peer[r]);
+  if (++c.p2p.seq == 0) c.p2p.seq = 2; /* 0 is the tag of the zero-initialised buffer; keep the parity sequence */
+  a.G = c.p2p.G; a.rank = c.rank; a.seq = c.p2p.seq; a.timeout_ns = c.p2p.timeout_ns;
+  const int grid = (int)((n + Ctx::P2P::kThreads - 1) / Ctx::P2P::kThreads);
+  if (slot_term) p2p_allreduce_kernel<true><<<grid, Ctx::P2P::kThreads, 0, c.stream>>>(a, buf, (int)n, partial, nblocks, nslots, slot_term);
+  else p2p_allreduce_kernel<false><<<grid, Ctx::P2P::kThreads, 0, c.stream>>>(a, buf, (int)n, nullptr, 0, 0, nullptr);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw CudaError(std::string("p2p_allreduce_kernel: ") + cudaGetErrorString(e));
+  ++c.launches;
+}
+
+bool Ctx::p2p_ok(size_t n) const { return p2p.G && p2p.enabled && n <= P2P::kCap; }
+
 void Ctx::allreduce_sum(double* buf, size_t n) {
-  if (nranks <= 1 || !comm) return;
+  if (nranks <= 1 || !comm || n == 0) return;
+  if (p2p_ok(n)) { p2p_launch(*this, buf, n, nullptr, 0, 0, nullptr); return; }
   NcclApi& api = NcclApi::get();
   const int rc = api.AllReduce(buf, buf, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
   if (rc != 0) throw NcclError(std::string("ncclAllReduce: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
@@ -1122,8 +1275,7 @@ void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Works
     else { if (g.prog_in_smem) OB_L2(2, true) else OB_L2(2, false) }
 #undef OB_L2
     check_launch(c, "phi_t2_kernel");
-    phi_t_reduce_kernel<<<(p.nslots + 127) / 128, 128, 0, c.stream>>>(p.partial, grid, p.nslots, pr.slot_term.p, out);
-    check_launch(c, "phi_t_reduce_kernel");
+    launch_phi_t_reduce(c, p.partial, grid, p.nslots, pr.slot_term.p, out);
     return;
   }
   PhiGeom g;
@@ -1149,11 +1301,16 @@ void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Works
 #undef OB_LAUNCH_T2
 #undef OB_LAUNCH_T
   check_launch(c, "phi_t_kernel");
-  phi_t_reduce_kernel<<<(p.nslots + 127) / 128, 128, 0, c.stream>>>(p.partial, grid, p.nslots, pr.slot_term.p, out);
-  check_launch(c, "phi_t_reduce_kernel");
+  launch_phi_t_reduce(c, p.partial, grid, p.nslots, pr.slot_term.p, out);
 }
 
 void launch_phi_t_reduce(Ctx& c, const double* partial, int nblocks, int nslots, const int32_t* slot_term, double* out) {
+  if (c.fuse_n) { /* the caller's allreduce of out[0..fuse_n) rides on this launch (Ctx::fuse_allreduce) */
+    p2p_launch(c, out, c.fuse_n, partial, nblocks, nslots, slot_term);
+    c.fuse_n = 0;
+    c.fused = true;
+    return;
+  }
   phi_t_reduce_kernel<<<(nslots + 127) / 128, 128, 0, c.stream>>>(partial, nblocks, nslots, slot_term, out);
   check_launch(c, "phi_t_reduce_kernel");
 }
