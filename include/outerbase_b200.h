@@ -189,6 +189,11 @@ int ob_outerbase_spec_state(ob_outerbase* ob, const uint64_t* terms, uint64_t K,
  * get the length; info = {types, accumulators per thread, tile rows Phi a, tile rows Phi^T}. */
 int ob_spec_source(const uint64_t* terms, uint64_t K, uint64_t d, const int* opts9, char* buf,
                    uint64_t* len, uint64_t* info /* 4 */);
+/* Test hook (no GPU needed): the source of the hyper-gradient sweep kernel (phi_d_spec: gradhyp of
+ * prodmmge_ / sqmm_gradhyp contracted with row weights, src/linalg.cpp:139-163, 225-277) for a table;
+ * info = {coefficient slots, tile rows}. */
+int ob_spec_source_dot(const uint64_t* terms, uint64_t K, uint64_t d, char* buf, uint64_t* len,
+                       uint64_t* info /* 2 */);
 /* Test hook (no GPU needed): compile a source for sm_100a with NVRTC, bypassing the disk
  * cache; returns the cubin size. */
 int ob_spec_compile_check(const char* source, uint64_t* cubin_bytes, double* seconds);

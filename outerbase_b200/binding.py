@@ -100,6 +100,16 @@ class Library:
         self.call("spec_source", _p(t), _u(t.shape[0]), _u(t.shape[1]), o, buf, C.byref(n), info)
         return buf.value.decode(), dict(types=info[0], nacc=info[1], tile_rows_a=info[2], tile_rows_t=info[3])
 
+    def spec_source_dot(self, terms):
+        """CUDA source of the hyper-gradient sweep kernel (phi_d_spec) for a terms table (host only) -> (source, info)."""
+        t = _terms(terms)
+        n = C.c_uint64(0)
+        info = (C.c_uint64 * 2)()
+        self.call("spec_source_dot", _p(t), _u(t.shape[0]), _u(t.shape[1]), None, C.byref(n), info)
+        buf = C.create_string_buffer(n.value)
+        self.call("spec_source_dot", _p(t), _u(t.shape[0]), _u(t.shape[1]), buf, C.byref(n), info)
+        return buf.value.decode(), dict(slots=info[0], tile_rows=info[1])
+
     def spec_compile_check(self, source: str):
         """NVRTC-compile a generated source for sm_100a (no GPU needed) -> (cubin bytes, seconds)."""
         nb, sec = C.c_uint64(0), C.c_double(0)

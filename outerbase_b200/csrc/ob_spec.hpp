@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -55,6 +56,20 @@ struct MatParams {
   unsigned off_phi, off_coef;
 };
 
+/* mirrored by `struct DotParams` in ob_spec_scaffold.inc (phi_d_spec) */
+struct DotParams {
+  const double* gmat;    /* basemat_gradhyp: column gest[h] + j = G_h[:, j], leading dimension ld */
+  const double* bmat;    /* squared operator: the PLAIN basemat (basematsq_gradhyp = 2 G % B, modandbase.cpp:588-590), else null */
+  const double* wdot;    /* row weights w (N) or null = ones */
+  double* partial;       /* H x gridDim per-CTA sums */
+  unsigned long long ld;
+  int H, d;
+  int hst[33];           /* hypst: first hyper-parameter of each dimension (d + 1) */
+  int gest[65];          /* first basemat_gradhyp column of each hyper-parameter */
+  int kst[33];           /* knotptst: first basemat column of each dimension */
+  unsigned off_hsm;      /* shared memory: per-warp sums, warps x H doubles */
+};
+
 struct SpecOptions {
   /* Phi a (one stream = the whole program): rows per lane, passes per tile (= warps per tile), tiles
    * in work at once (compute warps = qa * tga), register-cached columns */
@@ -71,6 +86,9 @@ struct SpecOptions {
   int ut = 1;
   /* multi-RHS kernel: compute warps (32 rows each) per tile and terms per block */
   int mw = 8, kc = 16;
+  /* hyper-gradient sweep (phi_d_spec): warps per tile, tiles in work, register-cached columns, most tile columns
+   * whose derivative accumulators still fit the register file */
+  int qd = 2, tgd = 3, cache_d = 10, maxcols_d = 96;
 };
 
 struct SpecSource {
@@ -291,6 +309,117 @@ inline int emit_mat(Emitter& e, const Program& P, int TR, int KC) {
   return n;
 }
 
+/* ---- reverse-mode sweep over the trie (phi_d_spec): for one row, yhat/basescale = sum_k a_k prod B and
+ *   D_c = d(yhat/basescale) / d B_c   for EVERY tile column c = (dimension, level),
+ * from one depth-first walk: descending an edge (parent -> child, column c) forms the prefix product
+ * v_child = v_parent * B_c, returning from it brings the child's Horner sum u_child = a_child + sum B u, and the edge
+ * contributes  u_parent += B_c u_child  and  D_c += v_parent u_child.  3 FMAs per inner edge, 2 per leaf, against the
+ * H separate plain products of domultgesub_ (src/linalg.cpp:139-163) this replaces.  The epilogue contracts D with the
+ * stored gradient columns per dimension (linalg.cpp:139-163, 273-276 regrouped):
+ *   outge[n,h] = basescale * ( sum_j D_(l,j) G_h[n,j] + G_h[n,0] (u_root - sum_j D_(l,j) B_(l,j)) ),   l = hypmatch[h]. */
+struct DNode { int col = -1, term = -1; std::vector<int> kids; };
+
+inline int emit_dot(Emitter& e, Emitter& tab, const Program& P, int TR, int cache) {
+  const size_t nc = P.cols.size();
+  /* trie of the terms' column paths (csr rows are ascending in dimension) */
+  std::vector<DNode> N(1);
+  for (u64 k = 0; k < P.K; ++k) {
+    int at = 0;
+    for (uint32_t i = P.csr_ptr[k]; i < P.csr_ptr[k + 1]; ++i) {
+      const int c = (int)P.csr_col[i];
+      int nx = -1;
+      for (int kid : N[at].kids) if (N[kid].col == c) { nx = kid; break; }
+      if (nx < 0) { nx = (int)N.size(); DNode nd; nd.col = c; N.push_back(nd); N[at].kids.push_back(nx); }
+      at = nx;
+    }
+    N[at].term = (int)k;
+  }
+  std::vector<int> use(nc, 1); /* the epilogue reads every column once */
+  for (size_t i = 1; i < N.size(); ++i) use[N[i].col]++;
+  std::vector<int> order(nc);
+  for (size_t i = 0; i < nc; ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return use[a] > use[b]; });
+  std::vector<char> cached(nc, 0);
+  for (int i = 0; i < (int)nc && i < cache; ++i) cached[order[i]] = 1;
+  auto fac = [&](int c) {
+    char b[64];
+    if (cached[c]) std::snprintf(b, sizeof b, "f%d", c);
+    else std::snprintf(b, sizeof b, "ldv(tp + %uu)", (unsigned)(c * TR) * 8u);
+    return std::string(b);
+  };
+  for (size_t c = 0; c < nc; ++c) if (cached[c]) e.f("const double f%d = lds(tp + %uu);\n", (int)c, (unsigned)(c * TR) * 8u);
+  for (size_t c = 0; c < nc; ++c) e.f("double D%d = 0.0;\n", (int)c);
+  /* coefficients in consumption order: slot i of the shared-memory copy holds a[dterm[i]] */
+  std::vector<int> dterm;
+  { /* pre-pass: the order in which the walk below consumes coefficients */
+    std::vector<std::pair<int, size_t>> st{{0, 0}};
+    if (N[0].term >= 0) dterm.push_back(N[0].term);
+    while (!st.empty()) {
+      auto& [n, i] = st.back();
+      if (i == N[n].kids.size()) { st.pop_back(); continue; }
+      const int kid = N[n].kids[i++];
+      if (N[kid].term >= 0) dterm.push_back(N[kid].term);
+      if (!N[kid].kids.empty()) st.push_back({kid, 0});
+    }
+  }
+  int slot = 0, nv = 0;
+  std::vector<char> have(dterm.size() + 2, 0);
+  auto coef = [&]() { /* next coefficient -> variable a<slot>; even slots fetch the aligned pair with one LDS.128 */
+    const int k = slot++;
+    if (!have[k]) {
+      if (!(k & 1) && k + 1 < (int)dterm.size()) { e.f("double a%d, a%d; lda2<%d>(as, a%d, a%d);\n", k, k + 1, 8 * k, k, k + 1); have[k] = have[k + 1] = 1; }
+      else { e.f("const double a%d = lda<%d>(as);\n", k, 8 * k); have[k] = 1; }
+    }
+    char b[24]; std::snprintf(b, sizeof b, "a%d", k); return std::string(b);
+  };
+  auto fresh = [&](const char* stem) { char b[24]; std::snprintf(b, sizeof b, "%s%d", stem, nv++); return std::string(b); };
+  /* returns the expression of the node's Horner sum u ("" = zero); v = prefix product at the node ("" = one) */
+  std::function<std::string(int, const std::string&)> walk = [&](int n, const std::string& v) -> std::string {
+    std::string u;
+    if (N[n].term >= 0) u = coef();
+    for (int kid : N[n].kids) {
+      const int c = N[kid].col;
+      std::string uc;
+      if (N[kid].kids.empty()) uc = coef(); /* leaf: its sum is its coefficient (a trie leaf is always a term) */
+      else {
+        std::string vc;
+        if (v.empty()) {
+          vc = fac(c);
+          if (!cached[c]) { const std::string t = fresh("v"); e.f("const double %s = %s;\n", t.c_str(), vc.c_str()); vc = t; }
+        } else { vc = fresh("v"); e.f("const double %s = %s * %s;\n", vc.c_str(), v.c_str(), fac(c).c_str()); }
+        uc = walk(kid, vc);
+      }
+      const std::string x = fresh("u");
+      if (u.empty()) e.f("const double %s = %s * %s;\n", x.c_str(), fac(c).c_str(), uc.c_str());
+      else e.f("const double %s = fma(%s, %s, %s);\n", x.c_str(), fac(c).c_str(), uc.c_str(), u.c_str());
+      u = x;
+      if (v.empty()) e.f("D%d += %s;\n", c, uc.c_str());
+      else e.f("D%d = fma(%s, %s, D%d);\n", c, v.c_str(), uc.c_str(), c);
+    }
+    return u;
+  };
+  const std::string root = walk(0, "");
+  e.f("const double uroot = %s;\n", root.empty() ? "0.0" : root.c_str());
+  if (slot != (int)dterm.size()) throw std::logic_error("phi_d_spec: coefficient order mismatch");
+  /* epilogue: one block per dimension; the hyper-parameters of a dimension are a run-time loop (their number
+   * belongs to the covariance functions, not to the terms table) */
+  for (u64 l = 0; l < P.d; ++l) {
+    std::vector<int> cl;
+    for (size_t c = 0; c < nc; ++c) if (P.cols[c].dim == l) cl.push_back((int)c);
+    if (cl.empty()) { e.f("OBS_D_DIM_EMPTY(%d)\n", (int)l); continue; }
+    e.f("{ double E = 0.0;\n");
+    for (int c : cl) e.f("E = fma(D%d, %s, E);\n", c, fac(c).c_str());
+    e.f("OBS_D_HYP_BEGIN(%d)\n", (int)l);
+    for (int c : cl) e.f("S = fma(D%d, OBS_D_G(%d, %u), S);\n", c, (int)l, P.cols[c].level);
+    e.f("OBS_D_HYP_END(%d)\n}\n", (int)l);
+  }
+  tab.f("__device__ const int obs_dterm[] = {");
+  for (int t : dterm) tab.f("%d,", t);
+  tab.f("0};\n");
+  for (size_t i = 0; i < dterm.size(); ++i) tab.f("// OBS_SLOT_D %d %d\n", (int)i, dterm[i]);
+  return (int)dterm.size();
+}
+
 inline void replace_marker(std::string& s, const char* marker, const std::string& with) {
   const size_t at = s.find(marker);
   if (at == std::string::npos) throw std::logic_error(std::string("scaffold marker missing: ") + marker);
@@ -458,6 +587,35 @@ inline SpecSource generate_mat(const Program& pa, const SpecOptions& opt) {
   std::string src = scaffold_text();
   replace_marker(src, "//@@TABLES@@", tab.s);
   replace_marker(src, "//@@BODY_M@@", body.s);
+  S.src = hdr.s + src;
+  S.ok = true;
+  return S;
+}
+
+/* the hyper-gradient module (phi_d_spec only): pa = program compiled with G = 1 (its column table and CSR) */
+inline SpecSource generate_dot(const Program& pa, const SpecOptions& opt) {
+  using namespace detail;
+  SpecSource S;
+  S.opt = opt;
+  S.tr_a = 32 * opt.qd;
+  if (!pa.fast_ok || pa.G != 1 || pa.tmem_cap || pa.K == 0 || pa.aug_dim >= 0) { S.why = "program does not match"; return S; }
+  if (256 % S.tr_a || opt.qd < 1 || opt.tgd < 1 || opt.tgd > 8 || opt.np < 1 || opt.qd * opt.tgd + opt.np > 8) { S.why = "inconsistent tile options"; return S; }
+  if ((int)pa.cols.size() > opt.maxcols_d || pa.d > 32) { S.why = "too many basis columns for the register-resident derivative accumulators"; return S; }
+  Emitter hdr, tab, body;
+  hdr.f("#define OBS_PARAM_BYTES %d\n#define OBS_DOT_BYTES %d\n#define OBS_K %llu\n#define OBS_NP %d\n#define OBS_HAVE_D 1\n#define OBS_NCOLS_A %d\n", (int)sizeof(SpecParams),
+        (int)sizeof(DotParams), (unsigned long long)pa.K, opt.np, (int)pa.cols.size());
+  hdr.f("#define OBS_QD %d\n#define OBS_TGD %d\n", opt.qd, opt.tgd);
+  tab.f("__device__ const unsigned short obs_cols_a[] = {");
+  for (size_t c = 0; c < pa.cols.size(); ++c) tab.f("%d,", (int)c);
+  tab.f("0};\n");
+  for (size_t c = 0; c < pa.cols.size(); ++c) tab.f("// OBS_LAYOUT_D %d %u %u\n", (int)c, pa.cols[c].dim, pa.cols[c].level);
+  body.f("/*BEGIN_BODY_D*/\n");
+  S.nacc = emit_dot(body, tab, pa, S.tr_a, opt.cache_d);
+  body.f("/*END_BODY_D*/\n");
+  if (S.nacc != (int)pa.K) { S.why = "coefficient count mismatch"; return S; }
+  std::string src = scaffold_text();
+  replace_marker(src, "//@@TABLES@@", tab.s);
+  replace_marker(src, "//@@BODY_D@@", body.s);
   S.src = hdr.s + src;
   S.ok = true;
   return S;

@@ -59,6 +59,27 @@ def main():
     if backend == "gloo":
         t = torch.from_numpy(part.copy()); dist.all_reduce(t); part = t.numpy()
     assert relerr(part, ref_ob.tmatmul(terms, r)) < 1e-9
+    if backend == "nccl":
+        # the cross-GPU sum itself: the one-shot peer-memory kernel (tagged 8-byte words, every rank adds the slots in
+        # rank order) against torch's own NCCL allreduce, bit-identical across ranks; a payload above its capacity and
+        # option p2p=0 both go through ncclAllReduce inside the library
+        for n, p2p in ((K, 1), (1, 1), (4097, 1), (70000, 1), (K, 0)):
+            lib.set_option("p2p", p2p)
+            for rep in range(3):  # consecutive calls alternate the slot parity
+                v = torch.from_numpy(np.random.default_rng([rank, n, rep]).normal(size=n)).cuda()
+                want = v.clone(); dist.all_reduce(want)
+                torch.cuda.synchronize()
+                lib.allreduce_dev(v.data_ptr(), n); lib.synchronize()
+                assert torch.allclose(v, want, rtol=1e-14, atol=1e-14), (n, p2p, rep)
+                tmax, tmin = v.clone(), v.clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+                assert torch.equal(tmax, tmin), (n, p2p, rep)
+        lib.set_option("p2p", 1)
+        # a rank WITHOUT rows takes the plain variant of the kernel while its peers run the fused reduce + allreduce
+        nb = N if rank == 0 else 0
+        obe = lib.outerbase(om, x[:nb] if rank == 0 else x[:0])
+        part = obe.tmatmul(terms, r[:nb])
+        assert relerr(part, ref_ob.tmatmul(terms, r)) < 1e-9
 
     # loglik_gauss / optcg on sharded rows
     ref = oracle.lpdfvec(oracle.logpr_gauss(omr, terms), oracle.loglik_gauss(omr, terms, y, x))
@@ -91,26 +112,6 @@ def main():
         tmax, tmin = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         assert torch.equal(tmax, tmin)
-        # the cross-GPU sum itself: the one-shot peer-memory kernel (tagged 8-byte words, every rank adds the slots in
-        # rank order) against torch's own NCCL allreduce, bit-identical across ranks; a payload above its capacity and
-        # option p2p=0 both go through ncclAllReduce inside the library
-        for n, p2p in ((K, 1), (1, 1), (4097, 1), (70000, 1), (K, 0)):
-            lib.set_option("p2p", p2p)
-            for rep in range(3):  # consecutive calls alternate the slot parity
-                v = torch.from_numpy(np.random.default_rng([rank, n, rep]).normal(size=n)).cuda()
-                want = v.clone(); dist.all_reduce(want)
-                torch.cuda.synchronize()
-                lib.allreduce_dev(v.data_ptr(), n); lib.synchronize()
-                assert torch.allclose(v, want, rtol=1e-14, atol=1e-14), (n, p2p, rep)
-                tmax, tmin = v.clone(), v.clone()
-                dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-                assert torch.equal(tmax, tmin), (n, p2p, rep)
-        lib.set_option("p2p", 1)
-        # a rank WITHOUT rows takes the plain variant of the kernel while its peers run the fused reduce + allreduce
-        nb = N if rank == 0 else 0
-        obe = lib.outerbase(om, x[:nb] if rank == 0 else x[:0])
-        part = obe.tmatmul(terms, r[:nb])
-        assert relerr(part, ref_ob.tmatmul(terms, r)) < 1e-9
     else:
         # the reduction loglik_gauss::update needs: grad (K) | ssq | row count, one allreduce
         lk = oracle.loglik_gauss(omr, terms, y[lo:hi], x[lo:hi])

@@ -10,7 +10,10 @@ REPO = Path(__file__).resolve().parents[1]
 
 
 def _run(backend, nproc, port):
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    # the oracle's OpenMP regions ask for omp_get_num_procs() threads each (modandbase.cpp:464): cap them, or nproc ranks
+    # oversubscribe the host nproc-fold and spin in each other's barriers
+    per_rank = str(max(2, (os.cpu_count() or 2) // nproc))
+    env = dict(os.environ, OMP_NUM_THREADS="2", OMP_THREAD_LIMIT=per_rank, OMP_WAIT_POLICY="passive")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(REPO / "tests" / "mgpu_worker.py"), backend]
     return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
