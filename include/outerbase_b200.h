@@ -179,7 +179,13 @@ int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uin
  *                      ($OB_SPEC_CACHE, default ~/.cache/outerbase_b200, "0" disables)
  * ob_outerbase_specialize compiles NOW for one table (like planning an FFT) and reports the
  * seconds spent compiling (0 on a cache hit).  Results of the two kernel families agree to
- * rounding (<= 1e-12 relative), not bitwise: the summation trees differ. */
+ * rounding (<= 1e-12 relative), not bitwise: the summation trees differ.
+ * Further options: "p2p" 1|0 -- the library's peer-memory allreduce or ncclAllReduce (see
+ * ob_ctx_allreduce_dev; the same value on every rank); "dsweep" 0|1 (env OB_DSWEEP) -- the
+ * hyper-gradients of a specialised table (prodmmge_ / sqmm_gradhyp contracted with row weights,
+ * src/linalg.cpp:139-163, 225-277; loglik_gauss.cpp:127; fit.cpp:259-263) from ONE reverse-mode
+ * sweep over the rows (kernel phi_d_spec) instead of one product per hyper-parameter.  dsweep is
+ * off by default: its generated code is verified on the CPU, the kernel has not been timed yet. */
 int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
 int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
 /* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */

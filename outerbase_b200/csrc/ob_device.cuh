@@ -75,6 +75,9 @@ struct Ctx {
    * (spec_work row-terms processed by the interpreter kernels) or its module is in the disk cache */
   int spec_mode = 2;
   double spec_work = 4e12;
+  /* hyper-gradients of a specialised table from one reverse-mode sweep (phi_d_spec) instead of one product per
+   * hyper-parameter: option "dsweep" / env OB_DSWEEP.  Off by default until it has been measured on a B200. */
+  bool dsweep = false;
   explicit Ctx(int dev);
   ~Ctx();
   void sync() { OB_CUDA(cudaStreamSynchronize(stream)); }
@@ -204,6 +207,17 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
 void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
 /* Phi . A on the FP64 tensor cores (phi_am_spec): A is K x C column-major (device), out N x C with leading dimension ldo.
  * The module is generated and compiled at first use.  Returns false when the tile does not fit (caller: column loop). */
+/* model-side tables of the hyper-gradient sweep (phi_d_spec): where the gradient columns of each hyper-parameter live */
+struct DotArgs {
+  const double* gmat = nullptr; /* basemat_gradhyp (leading dimension ld) */
+  const double* bmat = nullptr; /* squared operator: the plain basemat, else null */
+  u64 ld = 0;
+  int H = 0, d = 0;
+  const u64* hypst = nullptr;    /* d + 1 */
+  const u64* gest = nullptr;     /* H + 1 */
+  const u64* knotptst = nullptr; /* d + 1 */
+};
+bool launch_phi_d_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* a_dev, const double* w_dev, const DotArgs& g, double* out_dev);
 bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* A, u64 C, double* out, u64 ldo);
 /* coefficient blocks in emit order, columns of odd rows swizzled (ob_spec_scaffold.inc, phi_am_spec) */
 void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nrows, double* out);

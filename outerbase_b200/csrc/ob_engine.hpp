@@ -290,11 +290,31 @@ struct OuterBase {
    * dimension l's columns replaced by C_j = G_j - G_0 % B_j.  Same terms table => the specialised Phi a kernel runs it
    * with another column-pointer table; its PHI_DOT epilogue folds the dot with w, so yhatge is never stored.
    * Returns false when the table is not specialised (the caller then uses the augmented interpreter programs). */
+  /* The same H dots from ONE sweep over the rows (phi_d_spec, ob_spec_scaffold.inc: reverse-mode walk of the trie,
+   * d(Phi a)/dB for every basis column, contracted with the stored gradient columns per dimension), for the plain
+   * (sq = 0: loglik_gauss::update, loglik_gauss.cpp:127) and the squared operator (sq = 1: sqmm_gradhyp,
+   * modandbase.cpp:855-866, rows weighted by w or by one).  Option "dsweep" (Ctx::dsweep).  false: not available for
+   * this table -- the caller uses one product per hyper-parameter. */
+  bool gradhyp_sweep(const u64* terms, u64 K, int sq, const double* a_dev, const double* w_dev, double* out_dev /* H */) {
+    if (!ctx.dsweep || !dograd || H == 0) return false;
+    SpecEntry* e = spec_for(terms, K);
+    if (!e) return false;
+    obd::DotArgs g;
+    g.gmat = basematge.p; g.bmat = sq ? basemat.p : nullptr; g.ld = ld; g.H = (int)H; g.d = (int)d;
+    g.hypst = hypst.data(); g.gest = gest.data(); g.knotptst = knotptst.data();
+    return obd::launch_phi_d_spec(ctx, *e->k, plan(e->pa.get(), sq, -1), a_dev, w_dev, g, out_dev);
+  }
   bool gradhyp_dots_spec(const u64* terms, u64 K, const std::vector<double>& coeff_host, const double* w_dev, const double* yhat_dev,
                          double* out_dev /* H */) {
     if (!dograd || H == 0) return false;
     SpecEntry* e = spec_for(terms, K);
     if (!e) return false;
+    if (ctx.dsweep) {
+      tmpKd.upload(coeff_host, ctx.stream);
+      const bool done = gradhyp_sweep(terms, K, 0, tmpKd.p, w_dev, out_dev);
+      ctx.sync(); /* coeff_host must outlive the upload */
+      if (done) return true;
+    }
     const obt::Program& P = e->pa->host;
     const size_t nc = P.cols.size();
     std::vector<u64> lmax(d, 0);
@@ -583,6 +603,9 @@ struct Lpdf {
   virtual std::vector<double> diaghess() { return {}; }
   virtual std::vector<double> diaghessgradhyp() { return {}; } /* K x H */
   virtual std::vector<double> diaghessgradpara() { return {}; } /* K x npara */
+  /* out[h] = sum_k c[k] * diaghessgradhyp[k, h] without forming the K x H matrix, when the object can (lpdfvec's
+   * marginal adjustment, fit.cpp:259-263, only needs this contraction with c = 1 / diaghess) */
+  virtual bool diaghessgradhyp_dot(const std::vector<double>&, std::vector<double>&) { return false; }
   virtual void settotdiaghess(const std::vector<double>& dh) { totdiaghess = dh; didfulltothess = false; didnotothess = false; }
   virtual u64 nhyp() const { return 0; }
   virtual u64 nrow() const { return 0; }
@@ -696,6 +719,18 @@ struct LogprGauss : Lpdf { /* logpr_gauss.cpp:41-145 */
     const u64 K = nterms, H = om->nhyp();
     for (u64 h = 0; h < H; ++h) for (u64 i = 0; i < K; ++i) { const double s = coeffsd[i] * sca; o[i + h * K] = -(o[i + h * K] / (s * s)); }
     return o;
+  }
+  bool diaghessgradhyp_dot(const std::vector<double>& c, std::vector<double>& out) override {
+    const u64 K = nterms, H = om->nhyp();
+    if (c.size() != K) return false;
+    const std::vector<double> m = diaghessgradhyp();
+    out.assign(H, 0.0);
+    std::vector<double> t(K);
+    for (u64 h = 0; h < H; ++h) {
+      for (u64 i = 0; i < K; ++i) t[i] = m[i + h * K] * c[i];
+      out[h] = obh::sum2(t.data(), K);
+    }
+    return true;
   }
   std::vector<double> diaghessgradpara() override {
     std::vector<double> o(nterms);
@@ -848,6 +883,22 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     const double c = std::exp(-2 * para[0]);
     for (double& v : o) v = c * v;
     return o;
+  }
+  bool diaghessgradhyp_dot(const std::vector<double>& c, std::vector<double>& out) override {
+    /* sum_k c_k sum_n d(Phi^2)[n,k]/dhyp = sum_n d(Phi^2 c)[n]/dhyp: the hyper-gradient sweep on the squared operator */
+    const u64 K = nterms, H = ob.H;
+    if (!ctx.dsweep || c.size() != K || H == 0) return false;
+    kbuf.upload(c, ctx.stream);
+    red.ensure(H);
+    const bool done = ob.gradhyp_sweep(terms.data(), K, 1, kbuf.p, nullptr, red.p);
+    ctx.sync(); /* c must outlive the upload */
+    if (!done) return false;
+    ctx.allreduce_sum(red.p, H);
+    out.resize(H);
+    ob.d2h(out.data(), red.p, H);
+    const double sc = std::exp(-2 * para[0]);
+    for (double& v : out) v = sc * v;
+    return true;
   }
   std::vector<double> diaghessgradpara() override { /* :176-179 */
     std::vector<double> lh = sqcolsums();
@@ -1009,6 +1060,7 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
   std::vector<double> gradhyp_margadj, gradpara_margadj;
   bool domargadj = true;
   std::vector<double> diaghessv, diaghessgradhypv, diaghessgradparav;
+  bool hyp_matrix_stale = false; /* buildhess took the contracted route: the K x H matrix is formed on demand */
   bool redohess = true;
   Lpdf* kid[2];
   u64 parasrt[2], paraend[2];
@@ -1063,14 +1115,23 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
       diaghessv = diaghess_();
       settotdiaghess(diaghessv);
       if (domargadj) {
-        diaghessgradhypv = diaghessgradhyp_();
+        /* the marginal adjustment only needs diaghessgradhyp contracted with 1 / diaghess: children that can
+         * deliver that contraction directly (loglik_gauss: one sweep instead of 2H products) skip the K x H matrix,
+         * which is then formed lazily if somebody asks for it (diaghessgradhyp()) */
+        const u64 K = diaghessv.size();
+        std::vector<double> cinv(K), dot0, dot1;
+        for (u64 i = 0; i < K; ++i) cinv[i] = 1.0 / diaghessv[i];
+        const bool swept = kid[1]->diaghessgradhyp_dot(cinv, dot1) && kid[0]->diaghessgradhyp_dot(cinv, dot0) && dot0.size() == dot1.size();
+        if (swept) { diaghessgradhypv.clear(); hyp_matrix_stale = true; }
+        else { diaghessgradhypv = diaghessgradhyp_(); hyp_matrix_stale = false; }
         diaghessgradparav = diaghessgradpara_();
-        const u64 K = diaghessv.size(), H = diaghessgradhypv.size() / std::max<u64>(K, 1), P = para.size();
+        const u64 H = swept ? dot0.size() : diaghessgradhypv.size() / std::max<u64>(K, 1), P = para.size();
         std::vector<double> t(K);
         for (u64 i = 0; i < K; ++i) t[i] = std::log(diaghessv[i]);
         val_margadj = -0.5 * obh::sum2(t.data(), K);
         gradhyp_margadj.assign(H, 0.0);
         for (u64 h = 0; h < H; ++h) {
+          if (swept) { gradhyp_margadj[h] = -0.5 * (dot0[h] + dot1[h]); continue; }
           for (u64 i = 0; i < K; ++i) t[i] = diaghessgradhypv[i + h * K] / diaghessv[i];
           gradhyp_margadj[h] = -0.5 * obh::sum2(t.data(), K);
         }
@@ -1114,7 +1175,10 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
     return out;
   }
   std::vector<double> diaghess() override { return diaghessv; }
-  std::vector<double> diaghessgradhyp() override { return diaghessgradhypv; }
+  std::vector<double> diaghessgradhyp() override {
+    if (hyp_matrix_stale) { diaghessgradhypv = diaghessgradhyp_(); hyp_matrix_stale = false; }
+    return diaghessgradhypv;
+  }
   std::vector<double> diaghessgradpara() override { return diaghessgradparav; }
   double paralpdf(const double* p, u64 n) const override {
     if (n != para.size()) return -std::numeric_limits<double>::infinity();

@@ -896,6 +896,7 @@ Ctx::Ctx(int dev) : device(dev) {
   smem_optin = prop.sharedMemPerBlockOptin;
   OB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   OB_CUDA(cudaMallocHost(&pinned, 4096 * sizeof(double)));
+  if (const char* e = getenv("OB_DSWEEP")) dsweep = std::string(e) != "0";
   if (const char* e = getenv("OB_SPEC")) { /* 0 | 1 | auto */
     const std::string v(e);
     spec_mode = v == "0" ? 0 : (v == "1" ? 1 : 2);

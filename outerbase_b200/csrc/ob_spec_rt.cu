@@ -139,10 +139,16 @@ struct SpecKernels {
   int nblk = 0, mat_state = 0; /* 0 not built, 1 ready, -1 failed */
   size_t smem_m_set = 0;
   DevBuf<double> aperm;
+  /* hyper-gradient sweep module (phi_d_spec), built at first use */
+  cudaLibrary_t libd = nullptr;
+  cudaKernel_t kd = nullptr;
+  int dot_state = 0, tr_d = 0; /* 0 not built, 1 ready, -1 failed (too many columns for the register accumulators) */
+  size_t smem_d_set = 0;
+  DevBuf<double> dpart;
   obt::Program pa_host; /* copy of the G = 1 program the module is generated from */
   double compile_seconds = 0;
   bool from_cache = false;
-  ~SpecKernels() { if (lib) cudaLibraryUnload(lib); if (libm) cudaLibraryUnload(libm); }
+  ~SpecKernels() { if (lib) cudaLibraryUnload(lib); if (libm) cudaLibraryUnload(libm); if (libd) cudaLibraryUnload(libd); }
 };
 
 obs::SpecOptions spec_default_options() {
@@ -364,6 +370,74 @@ bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double*
     if (e != cudaSuccess) throw CudaError(std::string("phi_am_spec: ") + cudaGetErrorString(e));
     c.launches++;
   }
+  return true;
+}
+
+/* out[h] = sum over CTAs of partial[h * n + cta], fixed order */
+__global__ void sum_rows_kernel(const double* __restrict__ partial, int rows, int n, double* __restrict__ out) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= rows) return;
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += partial[(size_t)h * n + i];
+  out[h] = s;
+}
+
+/* gradhyp[h] = sum_n w_n * d(Phi a)[n]/d hyp_h for every hyper-parameter from ONE sweep over the rows (phi_d_spec,
+ * ob_spec_scaffold.inc): prodmmge_'s outge (src/linalg.cpp:225-277) contracted with the row weights, never stored.
+ * false: this table / model cannot use the kernel (too many basis columns for the register accumulators, more than
+ * 64 hyper-parameters or 32 dimensions, a column table with ops) -- the caller falls back to one product per hyper. */
+bool launch_phi_d_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* a, const double* w, const DotArgs& g, double* out) {
+  if (g.H == 0) return true;
+  if (g.H > 64 || g.d > 32) return false;
+  if (pl.cols->nload != pl.cols->ncol || pl.cols->has_ops) return false; /* stored columns only (basemat / basematsq) */
+  if (k.dot_state == 0) {
+    k.dot_state = -1;
+    obs::SpecSource S = obs::generate_dot(k.pa_host, k.opt);
+    if (!S.ok) return false;
+    double sec = 0;
+    bool cached = false;
+    const std::string cubin = spec_compile_source(S.src, &sec, &cached, false);
+    OB_CUDA(cudaLibraryLoadData(&k.libd, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    OB_CUDA(cudaLibraryGetKernel(&k.kd, k.libd, "phi_d_spec"));
+    k.tr_d = S.tr_a;
+    k.dot_state = 1;
+  }
+  if (k.dot_state != 1) return false;
+  if (pl.N == 0) { launch_fill(c, out, (u64)g.H, 0.0); return true; }
+  const int TR = k.tr_d, warps = k.opt.qd * k.opt.tgd;
+  obs::SpecParams p{};
+  spec_fill(p, pl, TR);
+  obs::DotParams q{};
+  const size_t vec_bytes = ((k.pa_host.K * sizeof(double) + 127) / 128) * 128;
+  const size_t hsm_bytes = (((size_t)warps * g.H * sizeof(double) + 127) / 128) * 128;
+  p.off_flags = 128;
+  p.off_vec = 128 + 256;
+  q.off_hsm = (unsigned)(p.off_vec + vec_bytes);
+  p.off_tile = (unsigned)(q.off_hsm + hsm_bytes);
+  p.tile_doubles = (unsigned)((p.ncol + 1) * TR);
+  const size_t tile_bytes = (size_t)p.tile_doubles * 8;
+  const size_t room = c.smem_optin > p.off_tile ? c.smem_optin - p.off_tile : 0;
+  p.nstage = (int)std::min<size_t>({(size_t)k.opt.tgd + 2, room / tile_bytes, (size_t)8});
+  if (p.nstage < k.opt.tgd) return false; /* tiles in work at once <= stages (mbarrier parity) */
+  const size_t smem = p.off_tile + (size_t)p.nstage * tile_bytes;
+  p.a = a;
+  const int grid = std::max(1, std::min(p.ntiles, c.sms));
+  q.gmat = g.gmat; q.bmat = g.bmat; q.wdot = w; q.ld = g.ld; q.H = g.H; q.d = g.d;
+  for (int l = 0; l <= g.d; ++l) { q.hst[l] = (int)g.hypst[l]; q.kst[l] = (int)g.knotptst[l]; }
+  for (int h = 0; h <= g.H; ++h) q.gest[h] = (int)g.gest[h];
+  q.partial = k.dpart.ensure((size_t)g.H * grid);
+  if (smem > k.smem_d_set) {
+    OB_CUDA(cudaFuncSetAttribute((const void*)k.kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k.smem_d_set = smem;
+  }
+  void* args[] = {&p, &q};
+  const cudaError_t e = cudaLaunchKernel((const void*)k.kd, dim3(grid), dim3(32 * (warps + k.opt.np)), args, smem, c.stream);
+  if (e != cudaSuccess) throw CudaError(std::string("phi_d_spec: ") + cudaGetErrorString(e));
+  c.launches++;
+  sum_rows_kernel<<<(g.H + 63) / 64, 64, 0, c.stream>>>(q.partial, g.H, grid, out);
+  const cudaError_t e2 = cudaGetLastError();
+  if (e2 != cudaSuccess) throw CudaError(std::string("sum_rows_kernel: ") + cudaGetErrorString(e2));
+  c.launches++;
   return true;
 }
 

@@ -3,6 +3,8 @@ the same C-ABI calls as tests/test_gpu_parity.py with the context option spec = 
 plain Phi a / Phi^T r product runs on the run-time compiled kernels.  Same tolerances: matvecs
 1e-12 relative on bit-identical basemat (north_star), fits 1e-8.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -149,6 +151,42 @@ def test_spec_loglik_and_optcg(spec, oracle):
     assert abs(vg.val - vo.val) <= 1e-8 * abs(vo.val)
     assert relerr(vg.coeff, vo.coeff) < 1e-8
     assert relerr(vg.gradhyp, vo.gradhyp) < 1e-6
+
+
+@pytest.mark.skipif(os.environ.get("OB_TEST_DSWEEP") != "1",
+                    reason="phi_d_spec (hyper-gradients in one sweep, option dsweep, off by default) has not run on a B200 yet: "
+                           "its generated code is checked on the CPU (tests/test_spec_generator.py); set OB_TEST_DSWEEP=1")
+def test_hyper_gradient_sweep(spec, oracle):
+    """Option dsweep: loglik_gauss::update's gradhyp (loglik_gauss.cpp:127) and lpdfvec's marginal adjustment
+    (fit.cpp:259-263, diaghessgradhyp contracted with 1 / diaghess) from ONE reverse-mode sweep each (phi_d_spec)
+    instead of H resp. 2H plain products -- same numbers as the per-hyper path and the oracle; the K x H matrix is
+    still available on demand."""
+    N, K = 10000, 1000
+    O = _lpdf_pair(oracle, N, K, "prior_first")
+    rng = O[4]
+    coeff = rng.normal(size=K) / 100
+    res = {}
+    for mode in (0, 1):
+        spec.set_option("dsweep", mode)
+        try:
+            G = _lpdf_pair(spec, N, K, "prior_first")
+            for T in ((O, G) if mode == 0 else (G,)):
+                T[6].compute_gradhyp = True; T[6].compute_gradpara = True
+                T[6].updatepara([np.log(0.1)])
+                T[6].update(coeff)
+                T[7].domarg = True
+                T[7].optcg(0.001, 100)
+            res[mode] = (np.array(G[6].gradhyp), np.array(G[7].gradhyp), G[7].val, G[7].cg_iters, np.array(G[7].diaghessgradhyp()))
+        finally:
+            spec.set_option("dsweep", 0)
+    lo, vo = O[6], O[7]
+    for mode in (0, 1):
+        lg, vg, val, iters, dgh = res[mode]
+        assert relerr(lg, lo.gradhyp) < 1e-7, mode
+        assert relerr(vg, vo.gradhyp) < 1e-6, mode
+        assert abs(val - vo.val) <= 1e-8 * abs(vo.val) and iters == vo.cg_iters
+        assert relerr(dgh, vo.diaghessgradhyp()) < 1e-7, mode
+    assert relerr(res[1][0], res[0][0]) < 1e-9 and relerr(res[1][1], res[0][1]) < 1e-8
 
 
 def test_spec_full_size_properties(spec):

@@ -124,3 +124,95 @@ def test_generated_statements_compute_phi(product_symbols, tmp_path):
             assert abs(accs[i] - bval * phi[k]) <= 1e-13 * abs(bval * phi[k]), (g, i, k)
         seen += tlist
     assert sorted(seen) == list(range(K))  # every term is owned by exactly one stream
+
+
+HARNESS_D = r"""
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+static const double* TILE;
+static const double* AS;
+static inline double lds(uint32_t a) { return TILE[a / 8]; }
+static inline double ldv(uint32_t a) { return TILE[a / 8]; }
+template <int OFF> static inline double lda(uint32_t) { return AS[OFF / 8]; }
+template <int OFF> static inline void lda2(uint32_t, double& x, double& y) { x = AS[OFF / 8]; y = AS[OFF / 8 + 1]; }
+using std::fma;
+static inline void hyp_add(double* dst, double v, int) { *dst += v; }
+struct DotParams { const double* gmat; const double* bmat; unsigned long long ld; int hst[33]; int gest[65]; int kst[33]; };
+%(macros)s
+extern "C" void run_d(const double* tile, const double* as_, const double* gmat, const double* bmat, const int* hst, int nd,
+                      const int* gest, int nh, const int* kst, double wv, double* hs, double* uroot_out) {
+  TILE = tile; AS = as_;
+  DotParams q{};
+  q.gmat = gmat; q.bmat = bmat; q.ld = 1;
+  for (int i = 0; i <= nd; ++i) { q.hst[i] = hst[i]; q.kst[i] = kst[i]; }
+  for (int i = 0; i <= nh; ++i) q.gest[i] = gest[i];
+  const uint32_t tp = 0, as = 0; (void)as;
+  const int lane = 0; const unsigned long long rw = 0;
+  {
+%(body)s
+  uroot_out[0] = uroot;
+  }
+}
+"""
+
+
+@pytest.mark.parametrize("unused_dim", [False, True])
+def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, unused_dim):
+    """phi_d_spec's generated body + epilogue macros (lifted to host C++) against the definition of prodmmge_'s outge
+    (src/linalg.cpp:139-163, 273-276) for one row, plain and squared (basematsq_gradhyp = 2 G % B, modandbase.cpp:588-590)."""
+    K, d = 160, 8
+    terms, rng = _terms(product_symbols, K, d)
+    if unused_dim:  # a dimension no term uses: its hyper-parameters still see G_h[:,0] * yhat
+        terms = np.asfortranarray(np.hstack([terms, np.zeros((K, 1), dtype=terms.dtype)]))
+        d += 1
+    src, info = product_symbols.spec_source_dot(terms)
+    assert "phi_d_spec" in src and info["slots"] == K
+    product_symbols.spec_compile_check(src)  # the real thing builds for sm_100a
+    TR = info["tile_rows"]
+    lay = [tuple(map(int, m)) for m in re.findall(r"// OBS_LAYOUT_D (\d+) (\d+) (\d+)", src)]
+    slots = [tuple(map(int, m)) for m in re.findall(r"// OBS_SLOT_D (\d+) (-?\d+)", src)]
+    body = re.search(r"/\*BEGIN_BODY_D\*/(.*?)/\*END_BODY_D\*/", src, re.S).group(1)
+    macros = re.search(r"(#define OBS_D_HYP_BEGIN.*?)__device__ __forceinline__ void hyp_add", src, re.S).group(1)
+    cpp = tmp_path / "harness_d.cpp"
+    cpp.write_text(HARNESS_D % dict(macros=macros, body=body))
+    so = tmp_path / "harness_d.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", str(so), str(cpp)], check=True)
+    lib = C.CDLL(str(so))
+    L = int(terms.max()) + 1
+    nh = 2  # hyper-parameters per dimension (mat25pow)
+    B = rng.uniform(0.5, 1.5, size=(d, L)); B[:, 0] = 1.0
+    G = rng.normal(size=(d * nh, L))  # G[h, j] = stored gradient column j of hyper h (level 0 included)
+    a = rng.normal(size=K)
+    T = np.array([np.prod([B[l, terms[k, l]] for l in range(d) if terms[k, l] > 0]) for k in range(K)])
+    hst = np.arange(0, nh * (d + 1), nh, dtype=np.int32)
+    gest = np.arange(0, L * (d * nh + 1), L, dtype=np.int32)
+    kst = np.arange(0, L * (d + 1), L, dtype=np.int32)
+    coef = np.zeros(K)
+    for i, t in slots:
+        coef[i] = a[t]
+    wv = 0.83
+    ptr = lambda v: v.ctypes.data_as(C.c_void_p)
+    for squared in (False, True):
+        Bt = B ** 2 if squared else B
+        Gt = 2 * G * np.repeat(B, nh, axis=0) if squared else G  # 2 G % B, level 0: B = 1
+        Tt = T ** 2 if squared else T
+        tile = np.zeros((len(lay) + 1) * TR)
+        for pos, dim, lev in lay:
+            tile[pos * TR] = Bt[dim, lev]
+        want = np.zeros(d * nh)
+        for h in range(d * nh):
+            l = h // nh
+            s = 0.0
+            for k in range(K):
+                j = terms[k, l]
+                if j > 0:
+                    s += a[k] * Tt[k] / Bt[l, j] * (Gt[h, j] - Gt[h, 0] * Bt[l, j])
+            want[h] = wv * (s + Gt[h, 0] * (Tt @ a))
+        hs = np.zeros(d * nh); uroot = np.zeros(1)
+        gflat = np.ascontiguousarray(G.ravel()); bflat = np.ascontiguousarray(B.ravel())
+        lib.run_d(ptr(tile), ptr(coef), ptr(gflat), ptr(bflat) if squared else None, ptr(hst), C.c_int(d), ptr(gest), C.c_int(d * nh),
+                  ptr(kst), C.c_double(wv), ptr(hs), ptr(uroot))
+        assert abs(uroot[0] - Tt @ a) <= 1e-12 * np.abs(Tt * a).sum()
+        scale = np.abs(want).max()
+        assert np.abs(hs - want).max() <= 1e-11 * scale, (squared, np.abs(hs - want).max(), scale)
