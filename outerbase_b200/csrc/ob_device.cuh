@@ -69,7 +69,7 @@ struct Ctx {
     void* local = nullptr;                     /* slots [parity 2][rank G][kCap] */
     void* peer[kMaxRanks] = {};                /* the same block of every rank, peer[rank] == local */
     unsigned seq = 0;                          /* tag of the current call (never 0) */
-    unsigned long long timeout_ns = 120ull * 1000000000ull;
+    unsigned long long timeout_ns = 300ull * 1000000000ull; /* a rank may sit in a run-time compile while its peers poll */
   } p2p;
   /* terms-specialised kernels (ob_spec.hpp): 0 never, 1 at first use, 2 once a table has proven hot
    * (spec_work row-terms processed by the interpreter kernels) or its module is in the disk cache */

@@ -10,6 +10,12 @@ import os
 import sys
 from pathlib import Path
 
+# the oracle's OpenMP regions ask for omp_get_num_procs() threads each: with one process per GPU they would
+# oversubscribe the host world-size-fold and spin in each other's barriers (an 8-rank run did not finish in 150 s)
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+os.environ.setdefault("OMP_THREAD_LIMIT", str(max(2, (os.cpu_count() or 2) // max(_world, 1))))
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 import numpy as np
 import torch
 import torch.distributed as dist
