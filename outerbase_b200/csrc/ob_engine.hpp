@@ -606,6 +606,7 @@ struct Lpdf {
   /* out[h] = sum_k c[k] * diaghessgradhyp[k, h] without forming the K x H matrix, when the object can (lpdfvec's
    * marginal adjustment, fit.cpp:259-263, only needs this contraction with c = 1 / diaghess) */
   virtual bool diaghessgradhyp_dot(const std::vector<double>&, std::vector<double>&) { return false; }
+  virtual bool can_diaghessgradhyp_dot() const { return false; }
   virtual void settotdiaghess(const std::vector<double>& dh) { totdiaghess = dh; didfulltothess = false; didnotothess = false; }
   virtual u64 nhyp() const { return 0; }
   virtual u64 nrow() const { return 0; }
@@ -720,6 +721,7 @@ struct LogprGauss : Lpdf { /* logpr_gauss.cpp:41-145 */
     for (u64 h = 0; h < H; ++h) for (u64 i = 0; i < K; ++i) { const double s = coeffsd[i] * sca; o[i + h * K] = -(o[i + h * K] / (s * s)); }
     return o;
   }
+  bool can_diaghessgradhyp_dot() const override { return true; }
   bool diaghessgradhyp_dot(const std::vector<double>& c, std::vector<double>& out) override {
     const u64 K = nterms, H = om->nhyp();
     if (c.size() != K) return false;
@@ -884,6 +886,7 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     for (double& v : o) v = c * v;
     return o;
   }
+  bool can_diaghessgradhyp_dot() const override { return ctx.dsweep; }
   bool diaghessgradhyp_dot(const std::vector<double>& c, std::vector<double>& out) override {
     /* sum_k c_k sum_n d(Phi^2)[n,k]/dhyp = sum_n d(Phi^2 c)[n]/dhyp: the hyper-gradient sweep on the squared operator */
     const u64 K = nterms, H = ob.H;
@@ -1121,7 +1124,8 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
         const u64 K = diaghessv.size();
         std::vector<double> cinv(K), dot0, dot1;
         for (u64 i = 0; i < K; ++i) cinv[i] = 1.0 / diaghessv[i];
-        const bool swept = kid[1]->diaghessgradhyp_dot(cinv, dot1) && kid[0]->diaghessgradhyp_dot(cinv, dot0) && dot0.size() == dot1.size();
+        const bool swept = kid[0]->can_diaghessgradhyp_dot() && kid[1]->can_diaghessgradhyp_dot() &&
+                           kid[1]->diaghessgradhyp_dot(cinv, dot1) && kid[0]->diaghessgradhyp_dot(cinv, dot0) && dot0.size() == dot1.size();
         if (swept) { diaghessgradhypv.clear(); hyp_matrix_stale = true; }
         else { diaghessgradhypv = diaghessgradhyp_(); hyp_matrix_stale = false; }
         diaghessgradparav = diaghessgradpara_();
