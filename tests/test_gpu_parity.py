@@ -305,6 +305,19 @@ def test_full_size_properties(gpu):
     assert np.all(s >= 0)
 
 
+def test_allreduce_dev_single_rank_is_the_identity(gpu):
+    """ob_ctx_allreduce_dev without a communicator: the sum over one rank leaves the buffer alone (the multi-rank
+    behaviour -- peer-memory kernel against NCCL, bit-identical across ranks -- is tests/mgpu_worker.py's)."""
+    import torch
+    v = torch.arange(5000, dtype=torch.float64, device="cuda") * 0.25
+    want = v.clone()
+    torch.cuda.synchronize()
+    gpu.allreduce_dev(v.data_ptr(), v.numel())
+    gpu.synchronize()
+    assert gpu.comm_info() == (1, 0)
+    assert torch.equal(v, want)
+
+
 @pytest.mark.parametrize("N,K", [(300, 40), (2000, 150)])
 def test_loglik_gda_parity(gpu, oracle, N, K):
     """loglik_gda (loglik_gda.cpp:47-239), residvar(_gradhyp) (modandbase.cpp:889-922) and pred_gda (:249-283): the
