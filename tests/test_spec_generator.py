@@ -157,11 +157,11 @@ extern "C" void run_d(const double* tile, const double* as_, const double* gmat,
 """
 
 
-@pytest.mark.parametrize("unused_dim", [False, True])
-def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, unused_dim):
+@pytest.mark.parametrize("K,d,unused_dim", [(160, 8, False), (160, 8, True), (2000, 10, False)])
+def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, K, d, unused_dim):
     """phi_d_spec's generated body + epilogue macros (lifted to host C++) against the definition of prodmmge_'s outge
-    (src/linalg.cpp:139-163, 273-276) for one row, plain and squared (basematsq_gradhyp = 2 G % B, modandbase.cpp:588-590)."""
-    K, d = 160, 8
+    (src/linalg.cpp:139-163, 273-276) for one row, plain and squared (basematsq_gradhyp = 2 G % B, modandbase.cpp:588-590);
+    the last case has the size of BASELINE config C3's table."""
     terms, rng = _terms(product_symbols, K, d)
     if unused_dim:  # a dimension no term uses: its hyper-parameters still see G_h[:,0] * yhat
         terms = np.asfortranarray(np.hstack([terms, np.zeros((K, 1), dtype=terms.dtype)]))
@@ -203,11 +203,9 @@ def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, unused_dim):
         want = np.zeros(d * nh)
         for h in range(d * nh):
             l = h // nh
-            s = 0.0
-            for k in range(K):
-                j = terms[k, l]
-                if j > 0:
-                    s += a[k] * Tt[k] / Bt[l, j] * (Gt[h, j] - Gt[h, 0] * Bt[l, j])
+            j = terms[:, l].astype(int)
+            m = j > 0
+            s = np.sum(a[m] * Tt[m] / Bt[l, j[m]] * (Gt[h, j[m]] - Gt[h, 0] * Bt[l, j[m]]))
             want[h] = wv * (s + Gt[h, 0] * (Tt @ a))
         hs = np.zeros(d * nh); uroot = np.zeros(1)
         gflat = np.ascontiguousarray(G.ravel()); bflat = np.ascontiguousarray(B.ravel())
@@ -216,3 +214,18 @@ def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, unused_dim):
         assert abs(uroot[0] - Tt @ a) <= 1e-12 * np.abs(Tt * a).sum()
         scale = np.abs(want).max()
         assert np.abs(hs - want).max() <= 1e-11 * scale, (squared, np.abs(hs - want).max(), scale)
+
+
+def test_hyper_gradient_sweep_refuses_tables_with_too_many_columns(product_symbols):
+    """The derivative accumulators live in registers: beyond 96 basis columns the generator declines and the engine
+    keeps one product per hyper-parameter (launch_phi_d_spec returns false)."""
+    d, L = 8, 14  # 8 x 13 = 104 columns
+    rows = [np.zeros(d, dtype=np.uint64)]
+    for l in range(d):
+        for j in range(1, L):
+            t = np.zeros(d, dtype=np.uint64); t[l] = j
+            rows.append(t)
+    terms = np.asfortranarray(np.array(rows, dtype=np.uint64))
+    with pytest.raises(ValueError):
+        product_symbols.spec_source_dot(terms)
+    product_symbols.spec_source(terms)  # the plain kernels have no such limit
