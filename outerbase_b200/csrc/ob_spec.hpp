@@ -362,18 +362,18 @@ inline int emit_dot(Emitter& e, Emitter& tab, const Program& P, int TR, int cach
       if (!N[kid].kids.empty()) st.push_back({kid, 0});
     }
   }
-  int slot = 0, nv = 0;
-  std::vector<char> have(dterm.size() + 2, 0);
+  int slot = 0, nv = 0, blk = 1;
+  std::vector<int> have(dterm.size() + 2, 0); /* block in which the coefficient's variable was declared */
   auto coef = [&]() { /* next coefficient -> variable a<slot>; even slots fetch the aligned pair with one LDS.128 */
     const int k = slot++;
-    if (!have[k]) {
-      if (!(k & 1) && k + 1 < (int)dterm.size()) { e.f("double a%d, a%d; lda2<%d>(as, a%d, a%d);\n", k, k + 1, 8 * k, k, k + 1); have[k] = have[k + 1] = 1; }
-      else { e.f("const double a%d = lda<%d>(as);\n", k, 8 * k); have[k] = 1; }
+    if (have[k] != blk) {
+      if (!(k & 1) && k + 1 < (int)dterm.size()) { e.f("double a%d, a%d; lda2<%d>(as, a%d, a%d);\n", k, k + 1, 8 * k, k, k + 1); have[k] = have[k + 1] = blk; }
+      else { e.f("const double a%d = lda<%d>(as);\n", k, 8 * k); have[k] = blk; }
     }
     char b[24]; std::snprintf(b, sizeof b, "a%d", k); return std::string(b);
   };
   auto fresh = [&](const char* stem) { char b[24]; std::snprintf(b, sizeof b, "%s%d", stem, nv++); return std::string(b); };
-  /* returns the expression of the node's Horner sum u ("" = zero); v = prefix product at the node ("" = one) */
+  /* returns the expression of the node's Horner sum u ("" = zero); v = prefix product at the node (never the root) */
   std::function<std::string(int, const std::string&)> walk = [&](int n, const std::string& v) -> std::string {
     std::string u;
     if (N[n].term >= 0) u = coef();
@@ -382,24 +382,43 @@ inline int emit_dot(Emitter& e, Emitter& tab, const Program& P, int TR, int cach
       std::string uc;
       if (N[kid].kids.empty()) uc = coef(); /* leaf: its sum is its coefficient (a trie leaf is always a term) */
       else {
-        std::string vc;
-        if (v.empty()) {
-          vc = fac(c);
-          if (!cached[c]) { const std::string t = fresh("v"); e.f("const double %s = %s;\n", t.c_str(), vc.c_str()); vc = t; }
-        } else { vc = fresh("v"); e.f("const double %s = %s * %s;\n", vc.c_str(), v.c_str(), fac(c).c_str()); }
+        const std::string vc = fresh("v");
+        e.f("const double %s = %s * %s;\n", vc.c_str(), v.c_str(), fac(c).c_str());
         uc = walk(kid, vc);
       }
       const std::string x = fresh("u");
       if (u.empty()) e.f("const double %s = %s * %s;\n", x.c_str(), fac(c).c_str(), uc.c_str());
       else e.f("const double %s = fma(%s, %s, %s);\n", x.c_str(), fac(c).c_str(), uc.c_str(), u.c_str());
       u = x;
-      if (v.empty()) e.f("D%d += %s;\n", c, uc.c_str());
-      else e.f("D%d = fma(%s, %s, D%d);\n", c, v.c_str(), uc.c_str(), c);
+      e.f("D%d = fma(%s, %s, D%d);\n", c, v.c_str(), uc.c_str(), c);
     }
     return u;
   };
-  const std::string root = walk(0, "");
-  e.f("const double uroot = %s;\n", root.empty() ? "0.0" : root.c_str());
+  /* The root's children are emitted as separate basic blocks behind an always-true, compiler-opaque branch
+   * (OBS_D_BLOCK): NVVM's time on ONE straight-line block of 10^4 statements is superlinear -- 28 s at C4's table
+   * against 6.5 s split.  Only ur, the D accumulators and the cached columns live across blocks; small sub-tries share
+   * a block.  Coefficient variables are block-local, so a pair loaded in one block is reloaded in the next. */
+  if (N[0].term >= 0) e.f("double ur = %s;\n", coef().c_str());
+  else e.f("double ur = 0.0;\n");
+  size_t mark = 0;
+  bool open = false;
+  auto lines_since = [&]() { size_t n = 0; for (size_t i = mark; i < e.s.size(); ++i) n += e.s[i] == '\n'; return n; };
+  for (int kid : N[0].kids) {
+    if (open && lines_since() > 300) { e.f("}\n"); open = false; }
+    if (!open) { ++blk; e.f("OBS_D_BLOCK {\n"); mark = e.s.size(); open = true; }
+    const int c = N[kid].col;
+    std::string uc;
+    if (N[kid].kids.empty()) uc = coef();
+    else {
+      std::string vc = fac(c);
+      if (!cached[c]) { const std::string t = fresh("v"); e.f("const double %s = %s;\n", t.c_str(), vc.c_str()); vc = t; }
+      uc = walk(kid, vc);
+    }
+    e.f("ur = fma(%s, %s, ur);\n", fac(c).c_str(), uc.c_str());
+    e.f("D%d += %s;\n", c, uc.c_str());
+  }
+  if (open) e.f("}\n");
+  e.f("const double uroot = ur;\n");
   if (slot != (int)dterm.size()) throw std::logic_error("phi_d_spec: coefficient order mismatch");
   /* epilogue: one block per dimension; the hyper-parameters of a dimension are a run-time loop (their number
    * belongs to the covariance functions, not to the terms table) */

@@ -153,10 +153,11 @@ struct SpecKernels {
 
 obs::SpecOptions spec_default_options() {
   obs::SpecOptions o;
-  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc -- tuning only */
-    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut, &o.mw, &o.kc};
+  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc,qd,tgd,cache_d,maxcols_d -- tuning only */
+    int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut, &o.mw, &o.kc,
+                &o.qd, &o.tgd, &o.cache_d, &o.maxcols_d};
     int i = 0;
-    for (const char* p = e; *p && i < 14; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (const char* p = e; *p && i < 18; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
   }
   return o;
 }

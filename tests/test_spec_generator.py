@@ -139,6 +139,7 @@ template <int OFF> static inline void lda2(uint32_t, double& x, double& y) { x =
 using std::fma;
 static inline void hyp_add(double* dst, double v, int) { *dst += v; }
 struct DotParams { const double* gmat; const double* bmat; unsigned long long ld; int hst[33]; int gest[65]; int kst[33]; };
+static struct { int ntiles = 1; } p;
 %(macros)s
 extern "C" void run_d(const double* tile, const double* as_, const double* gmat, const double* bmat, const int* hst, int nd,
                       const int* gest, int nh, const int* kst, double wv, double* hs, double* uroot_out) {
