@@ -429,7 +429,7 @@ inline int emit_dot(Emitter& e, Emitter& tab, const Program& P, int TR, int cach
     e.f("{ double E = 0.0;\n");
     for (int c : cl) e.f("E = fma(D%d, %s, E);\n", c, fac(c).c_str());
     e.f("OBS_D_HYP_BEGIN(%d)\n", (int)l);
-    for (int c : cl) e.f("S = fma(D%d, OBS_D_G(%d, %u), S);\n", c, (int)l, P.cols[c].level);
+    for (int c : cl) e.f("OBS_D_ACC(D%d, %d, %u)\n", c, (int)l, P.cols[c].level);
     e.f("OBS_D_HYP_END(%d)\n}\n", (int)l);
   }
   tab.f("__device__ const int obs_dterm[] = {");

@@ -158,8 +158,8 @@ extern "C" void run_d(const double* tile, const double* as_, const double* gmat,
 """
 
 
-@pytest.mark.parametrize("K,d,unused_dim", [(160, 8, False), (160, 8, True), (2000, 10, False)])
-def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, K, d, unused_dim):
+@pytest.mark.parametrize("K,d,unused_dim,nh", [(160, 8, False, 2), (160, 8, True, 2), (160, 8, False, 1), (160, 8, True, 3), (2000, 10, False, 2)])
+def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, K, d, unused_dim, nh):
     """phi_d_spec's generated body + epilogue macros (lifted to host C++) against the definition of prodmmge_'s outge
     (src/linalg.cpp:139-163, 273-276) for one row, plain and squared (basematsq_gradhyp = 2 G % B, modandbase.cpp:588-590);
     the last case has the size of BASELINE config C3's table."""
@@ -181,7 +181,7 @@ def test_generated_hyper_gradient_sweep(product_symbols, tmp_path, K, d, unused_
     subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", str(so), str(cpp)], check=True)
     lib = C.CDLL(str(so))
     L = int(terms.max()) + 1
-    nh = 2  # hyper-parameters per dimension (mat25pow)
+    # nh hyper-parameters per dimension (mat25pow: 2, mat25: 1); the epilogue takes them two at a time
     B = rng.uniform(0.5, 1.5, size=(d, L)); B[:, 0] = 1.0
     G = rng.normal(size=(d * nh, L))  # G[h, j] = stored gradient column j of hyper h (level 0 included)
     a = rng.normal(size=K)
