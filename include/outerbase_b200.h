@@ -185,7 +185,8 @@ int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uin
  * hyper-gradients of a specialised table (prodmmge_ / sqmm_gradhyp contracted with row weights,
  * src/linalg.cpp:139-163, 225-277; loglik_gauss.cpp:127; fit.cpp:259-263) from ONE reverse-mode
  * sweep over the rows (kernel phi_d_spec) instead of one product per hyper-parameter.  dsweep is
- * off by default: its generated code is verified on the CPU, the kernel has not been timed yet. */
+ * on by default (same value on every rank; a rank whose module fails to build makes all ranks fall
+ * back to the per-hyper products together). */
 int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
 int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
 /* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */

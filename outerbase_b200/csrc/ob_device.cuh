@@ -76,8 +76,10 @@ struct Ctx {
   int spec_mode = 2;
   double spec_work = 4e12;
   /* hyper-gradients of a specialised table from one reverse-mode sweep (phi_d_spec) instead of one product per
-   * hyper-parameter: option "dsweep" / env OB_DSWEEP.  Off by default until it has been measured on a B200. */
-  bool dsweep = false;
+   * hyper-parameter: option "dsweep" / env OB_DSWEEP (same value on every rank).  On by default: measured on a B200 in
+   * round 2 (profiles/r02_dsweep.json: one C3 objective evaluation 43.4 -> 25.8 ms, parity 9e-16 against the per-hyper
+   * path).  A rank that cannot run the sweep (module build failure) makes ALL ranks fall back together. */
+  bool dsweep = true;
   explicit Ctx(int dev);
   ~Ctx();
   void sync() { OB_CUDA(cudaStreamSynchronize(stream)); }

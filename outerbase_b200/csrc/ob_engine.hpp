@@ -139,6 +139,9 @@ struct OuterBase {
   /* outerbase::build (modandbase.cpp:547-626): re-reads the CURRENT state of om */
   void build() {
     if (!om) throw std::logic_error("this outerbase wraps caller-provided matrices");
+    if (knotptst != om->knotptst || d != om->d) { /* cached programs were bounds-checked against the OLD knot counts */
+      coltables.clear(); programs.clear(); specs.clear();
+    }
     d = om->d; hypmatch = om->hypmatch; hypst = om->hypst; gest = om->gest; knotptst = om->knotptst; /* setvals_ :492 */
     H = hypmatch.size();
     M = om->nknot();
@@ -522,7 +525,7 @@ struct OuterBase {
     for (u64 c = 0; c < C; ++c) mm_dev(terms, K, sq, A_dev + c * K, out_dev + c * ldo);
   }
   void tmm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 lda, u64 C, double* out_dev) {
-    for (u64 c = 0; c < C; ++c) tmm_dev(terms, K, sq, A_dev + c * lda, out_dev + c * K, false, c + 1 < C ? ld : lda);
+    for (u64 c = 0; c < C; ++c) tmm_dev(terms, K, sq, A_dev + c * lda, out_dev + c * K, false, std::min<u64>(ld, (C - c) * lda));
     ctx.allreduce_sum(out_dev, K * C);
   }
   void mm_mat(int sq, const u64* terms, u64 K, const double* A, u64 C, double* out) {
@@ -888,17 +891,26 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
   }
   bool can_diaghessgradhyp_dot() const override { return ctx.dsweep; }
   bool diaghessgradhyp_dot(const std::vector<double>& c, std::vector<double>& out) override {
-    /* sum_k c_k sum_n d(Phi^2)[n,k]/dhyp = sum_n d(Phi^2 c)[n]/dhyp: the hyper-gradient sweep on the squared operator */
+    /* sum_k c_k sum_n d(Phi^2)[n,k]/dhyp = sum_n d(Phi^2 c)[n]/dhyp: the hyper-gradient sweep on the squared operator.
+     * The swept / not-swept decision is COLLECTIVE: slot H of the reduction buffer counts the ranks whose sweep was
+     * unavailable (module build failure, table not specialised, geometry), so every rank takes the same branch and the
+     * allreduce sequence stays aligned (the fallback is a K*(1+H) allreduce in diaghessgradhyp()). */
     const u64 K = nterms, H = ob.H;
     if (!ctx.dsweep || c.size() != K || H == 0) return false;
     kbuf.upload(c, ctx.stream);
-    red.ensure(H);
-    const bool done = ob.gradhyp_sweep(terms.data(), K, 1, kbuf.p, nullptr, red.p);
+    red.ensure(H + 1);
+    OB_CUDA(cudaMemsetAsync(red.p, 0, (H + 1) * sizeof(double), ctx.stream));
+    bool done = false;
+    try { done = ob.gradhyp_sweep(terms.data(), K, 1, kbuf.p, nullptr, red.p); } catch (const std::exception&) { done = false; }
     ctx.sync(); /* c must outlive the upload */
-    if (!done) return false;
-    ctx.allreduce_sum(red.p, H);
-    out.resize(H);
-    ob.d2h(out.data(), red.p, H);
+    if (ctx.nranks > 1) {
+      if (!done) obd::launch_fill(ctx, red.p, H + 1, 0.0), obd::launch_fill(ctx, red.p + H, 1, 1.0);
+      ctx.allreduce_sum(red.p, H + 1);
+    } else if (!done) return false;
+    std::vector<double> r(H + 1);
+    ob.d2h(r.data(), red.p, H + 1);
+    if (r[H] != 0.0) return false; /* some rank could not sweep: all ranks fall back together */
+    out.assign(r.begin(), r.begin() + H);
     const double sc = std::exp(-2 * para[0]);
     for (double& v : out) v = sc * v;
     return true;

@@ -125,6 +125,36 @@ std::string spec_compile_nocache(const std::string& src, double* seconds) {
   return spec_compile_source(src, seconds, nullptr, false, /*use_cache=*/false);
 }
 
+/* forget a cached module that the driver refused to load (truncated or stale file) */
+static void spec_cache_evict(const std::string& src) {
+  NvrtcApi& api = NvrtcApi::get();
+  int vmaj = 0, vmin = 0;
+  if (api.ok() && api.Version) api.Version(&vmaj, &vmin);
+  char key[64];
+  std::snprintf(key, sizeof key, "%016llx_%d_%d.cubin", (unsigned long long)fnv1a(src), vmaj, vmin);
+  const std::string dir = cache_dir();
+  if (!dir.empty()) unlink((dir + "/" + key).c_str());
+}
+
+/* source -> loaded library.  A cubin that came from the disk cache and does not load is evicted and compiled once
+ * more; every other failure throws (callers of the lazily built modules catch and fall back). */
+static cudaLibrary_t spec_load_library(Ctx& c, const std::string& src, bool only_if_cached, double* seconds, bool* from_cache) {
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    bool cached = false;
+    const std::string cubin = spec_compile_source(src, seconds, &cached, only_if_cached);
+    if (from_cache) *from_cache = cached;
+    if (cubin.empty()) return nullptr;
+    OB_CUDA(cudaSetDevice(c.device));
+    cudaLibrary_t lib = nullptr;
+    const cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) return lib;
+    (void)cudaGetLastError();
+    if (!cached || attempt == 1) throw CudaError(std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
+    spec_cache_evict(src);
+  }
+  return nullptr;
+}
+
 struct SpecKernels {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t ka = nullptr, kt = nullptr;
@@ -148,6 +178,7 @@ struct SpecKernels {
   obt::Program pa_host; /* copy of the G = 1 program the module is generated from */
   double compile_seconds = 0;
   bool from_cache = false;
+  std::string lazy_why; /* why a lazily built module (phi_am_spec, phi_d_spec) is unavailable */
   ~SpecKernels() { if (lib) cudaLibraryUnload(lib); if (libm) cudaLibraryUnload(libm); if (libd) cudaLibraryUnload(libd); }
 };
 
@@ -170,10 +201,8 @@ std::shared_ptr<SpecKernels> spec_build(Ctx& c, const obt::Program& pa, const ob
   k->opt = opt; k->types = types; k->tr_a = S.tr_a; k->tr_t = S.tr_t; k->maxcols_t = S.maxcols_t; k->cluster = S.cluster;
   k->vec_bytes_a = ((pa.nslots() * sizeof(double) + 127) / 128) * 128;
   k->pa_host = pa;
-  const std::string cubin = spec_compile_source(S.src, &k->compile_seconds, &k->from_cache, only_if_cached);
-  if (cubin.empty()) return nullptr;
-  OB_CUDA(cudaSetDevice(c.device));
-  OB_CUDA(cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  k->lib = spec_load_library(c, S.src, only_if_cached, &k->compile_seconds, &k->from_cache);
+  if (!k->lib) return nullptr;
   OB_CUDA(cudaLibraryGetKernel(&k->ka, k->lib, "phi_a_spec"));
   OB_CUDA(cudaLibraryGetKernel(&k->kt, k->lib, "phi_t_spec"));
   return k;
@@ -333,11 +362,13 @@ bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double*
     k.mat_state = -1;
     obs::SpecSource S = obs::generate_mat(k.pa_host, k.opt);
     if (!S.ok) return false;
-    double sec = 0;
-    bool cached = false;
-    const std::string cubin = spec_compile_source(S.src, &sec, &cached, false);
-    OB_CUDA(cudaLibraryLoadData(&k.libm, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    OB_CUDA(cudaLibraryGetKernel(&k.km, k.libm, "phi_am_spec"));
+    try { /* a failed build leaves state -1: the caller runs the column loop, now and later */
+      k.libm = spec_load_library(c, S.src, false, nullptr, nullptr);
+      OB_CUDA(cudaLibraryGetKernel(&k.km, k.libm, "phi_am_spec"));
+    } catch (const std::exception& ex) {
+      k.lazy_why = std::string("phi_am_spec: ") + ex.what();
+      return false;
+    }
     k.nblk = S.nacc;
     k.mat_state = 1;
   }
@@ -395,11 +426,13 @@ bool launch_phi_d_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
     k.dot_state = -1;
     obs::SpecSource S = obs::generate_dot(k.pa_host, k.opt);
     if (!S.ok) return false;
-    double sec = 0;
-    bool cached = false;
-    const std::string cubin = spec_compile_source(S.src, &sec, &cached, false);
-    OB_CUDA(cudaLibraryLoadData(&k.libd, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    OB_CUDA(cudaLibraryGetKernel(&k.kd, k.libd, "phi_d_spec"));
+    try { /* a failed build leaves state -1: the caller runs one product per hyper-parameter, now and later */
+      k.libd = spec_load_library(c, S.src, false, nullptr, nullptr);
+      OB_CUDA(cudaLibraryGetKernel(&k.kd, k.libd, "phi_d_spec"));
+    } catch (const std::exception& ex) {
+      k.lazy_why = std::string("phi_d_spec: ") + ex.what();
+      return false;
+    }
     k.tr_d = S.tr_a;
     k.dot_state = 1;
   }

@@ -183,10 +183,26 @@ def genknotlist(bassize, x):
     return out
 
 
+# bounds of the covariance classes (covfuncs.cpp:109-110, 193-194, 281-282)
+_COV_BOUNDS = {"mat25": (0.0, 1.0), "mat25pow": (0.0, 1.0), "mat25ang": (0.0, 6.283185)}
+
+
+def checkcov(covname, x):
+    """.checkcov, R/fitting.R:158-175: the column must lie inside the covariance's bounds and span 1/20 of them."""
+    if covname not in _COV_BOUNDS:
+        raise ValueError("\n covariances must be from listcov()")
+    lo, hi = _COV_BOUNDS[covname]
+    x = np.asarray(x)
+    if x.min() < lo or x.max() > hi:
+        raise ValueError(f"\n x ranges exceed limits of covariance functions \n the limits are between {lo} and {hi} \n try rescaling")
+    if x.max() - x.min() < (hi - lo) / 20:
+        raise ValueError(f"\n x are too small for ranges\n the limits are between {lo} and {hi} \n try rescaling")
+
+
 def getsteps(numb, sampsize, sigtonoiseratio=1e-3, tol=0.001):
     """.getsteps, R/fitting.R:188-195 (its result is unused upstream: SURVEY A9.i)."""
     r = math.sqrt(numb / sampsize)
-    kapp = min(1000.0, (1 + r) ** 2 / (1 - r) ** 2)
+    kapp = 1000.0 if r == 1.0 else min(1000.0, (1 + r) ** 2 / (1 - r) ** 2)  # R: x/0 = Inf, min(1000, Inf) = 1000
     iterest = 0.5 * math.sqrt(kapp) * math.log(2 * sampsize * sigtonoiseratio / tol)
     return math.ceil(2 * iterest)
 
@@ -247,6 +263,8 @@ def obfit(lib, x, y, numb=100, verbose=0, covnames=None, hyp=None, numberopts=2,
     covnames = list(covnames) if covnames is not None else ["mat25pow"] * d
     if len(covnames) != d:
         raise ValueError("cov names must be same size as columns in x")
+    for k in range(d):  # R/fitting.R:68
+        checkcov(covnames[k], x[:, k])
     om = lib.outermod()
     om.setcovfs(covnames)
     if hyp is not None and len(hyp) == gethyp(om).size:

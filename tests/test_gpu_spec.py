@@ -153,11 +153,8 @@ def test_spec_loglik_and_optcg(spec, oracle):
     assert relerr(vg.gradhyp, vo.gradhyp) < 1e-6
 
 
-@pytest.mark.skipif(os.environ.get("OB_TEST_DSWEEP") != "1",
-                    reason="phi_d_spec (hyper-gradients in one sweep, option dsweep, off by default) has not run on a B200 yet: "
-                           "its generated code is checked on the CPU (tests/test_spec_generator.py); set OB_TEST_DSWEEP=1")
 def test_hyper_gradient_sweep(spec, oracle):
-    """Option dsweep: loglik_gauss::update's gradhyp (loglik_gauss.cpp:127) and lpdfvec's marginal adjustment
+    """Option dsweep (on by default since round 2): loglik_gauss::update's gradhyp (loglik_gauss.cpp:127) and lpdfvec's marginal adjustment
     (fit.cpp:259-263, diaghessgradhyp contracted with 1 / diaghess) from ONE reverse-mode sweep each (phi_d_spec)
     instead of H resp. 2H plain products -- same numbers as the per-hyper path and the oracle; the K x H matrix is
     still available on demand."""
@@ -178,7 +175,7 @@ def test_hyper_gradient_sweep(spec, oracle):
                 T[7].optcg(0.001, 100)
             res[mode] = (np.array(G[6].gradhyp), np.array(G[7].gradhyp), G[7].val, G[7].cg_iters, np.array(G[7].diaghessgradhyp()))
         finally:
-            spec.set_option("dsweep", 0)
+            spec.set_option("dsweep", 1)
     lo, vo = O[6], O[7]
     for mode in (0, 1):
         lg, vg, val, iters, dgh = res[mode]
