@@ -36,6 +36,19 @@ double dot2(const double* x, const double* y, u64 n) {
   return acc1 + acc2;
 }
 
+/* What Armadillo hands to BLAS is restated in the order of netlib's reference BLAS -- R's bundled libRblas, the
+ * implementation `PKG_LIBS = $(BLAS_LIBS)` (src/Makevars:13) links by default: ddot and dgemv('T') accumulate LEFT TO
+ * RIGHT in one accumulator.  Call sites: `x.t() * M` (gemv: linalg.cpp:574, logpr_gauss.cpp:103, loglik_gauss.cpp:127,
+ * loglik_gda.cpp:139-150) always; `dot(x, y)` (linalg.cpp:382-384) above 32 elements -- op_dot::direct_dot runs
+ * Armadillo's own two-accumulator loop up to 32.  oracle/_ref (the unmodified reference sources on the Armadillo
+ * shim, ARMA_SHIM_BLAS=1) makes the same choice; tests/test_oracle_ref.py holds the two bitwise equal. */
+double dot_seq(const double* x, const double* y, u64 n) {
+  double s = 0;
+  for (u64 i = 0; i < n; ++i) s = s + x[i] * y[i];
+  return s;
+}
+double dot_arma(const double* x, const double* y, u64 n) { return n <= 32 ? dot2(x, y, n) : dot_seq(x, y, n); }
+
 static bool all_finite(const vec& v) {
   for (double x : v) if (!std::isfinite(x)) return false;
   return true;
@@ -815,9 +828,9 @@ static void dotmultge_block(double* out, mat& outge, const double* b, const umat
     for (u64 l = 0; l < H; ++l) {
       if (terms(k, hypmatch[l]) > 0) {
         term_product_from(tempalt.data(), b, terms, k, knotptst, bm, n, (i64)hypmatch[l]);
-        outge(k, l) += dot2(tempalt.data(), bmge.col(gest[l] + terms(k, hypmatch[l])), n);
+        outge(k, l) += dot_arma(tempalt.data(), bmge.col(gest[l] + terms(k, hypmatch[l])), n);
       } else {
-        outge(k, l) += dot2(temp.data(), bmge.col(gest[l]), n);
+        outge(k, l) += dot_arma(temp.data(), bmge.col(gest[l]), n);
       }
     }
   }
@@ -938,7 +951,7 @@ void tprodmm_mat_(mat& out, const umat& terms, const mat& a, const mat& basemat,
         temp_.resize(n);
         for (u64 k = 0; k < K; ++k) { /* out.row(k) += temp.t() * b_ :574 */
           term_product(temp_.data(), 1.0, terms, k, knotptst, bm, n);
-          for (u64 c = 0; c < C; ++c) loc[tid](k, c) += dot2(temp_.data(), b.col(c) + s, n);
+          for (u64 c = 0; c < C; ++c) loc[tid](k, c) += dot_seq(temp_.data(), b.col(c) + s, n);
         }
       }
 #pragma omp barrier
@@ -951,7 +964,7 @@ void tprodmm_mat_(mat& out, const umat& terms, const mat& a, const mat& basemat,
         vec temp(N);
         for (u64 k = k0; k < k1; ++k) {
           term_product(temp.data(), 1.0, terms, k, knotptst, basemat, N);
-          for (u64 c = 0; c < C; ++c) out(k, c) += dot2(temp.data(), b.col(c), N);
+          for (u64 c = 0; c < C; ++c) out(k, c) += dot_seq(temp.data(), b.col(c), N);
         }
       },
       [&](int) {});
@@ -1182,7 +1195,7 @@ void logpr_gauss::update(const vec& coeff_) { /* :98-106 */
     for (u64 i = 0; i < K; ++i) t[i] = stdresid[i] * stdresid[i] - 1;
     for (u64 h = 0; h < H; ++h) {
       for (u64 i = 0; i < K; ++i) t2[i] = 0.5 * coefflvarge(i, h);
-      gradhyp[h] = dot2(t2.data(), t.data(), K);
+      gradhyp[h] = dot_seq(t2.data(), t.data(), K);
     }
   }
   if (compute_gradpara) {
@@ -1256,7 +1269,7 @@ void loglik_gauss::update(const vec& coeff_) { /* :110-130 */
     ob.tmm(grad, terms, residtemp);
     if (compute_gradhyp) {
       gradhyp.assign(ob.n_hyp, 0.0);
-      for (u64 h = 0; h < ob.n_hyp; ++h) gradhyp[h] = dot2(residtemp.data(), yhatge.col(h), N);
+      for (u64 h = 0; h < ob.n_hyp; ++h) gradhyp[h] = dot_seq(residtemp.data(), yhatge.col(h), N);
     }
     if (compute_gradpara) gradpara = {accu2(residtemp2.data(), N) - double(N)};
   }
@@ -1343,18 +1356,18 @@ void loglik_gda::update(const vec& coeff_) { /* :116-149 */
     if (compute_gradhyp) {
       gradhyp.assign(ob.n_hyp, 0.0);
       for (u64 h = 0; h < ob.n_hyp; ++h) {
-        gradhyp[h] = dot2(residtemp.data(), yhatge.col(h), N);
+        gradhyp[h] = dot_seq(residtemp.data(), yhatge.col(h), N);
         if (doda) {
-          gradhyp[h] += dot2(residtemp2.data(), obssd_gradhyp.col(h), N);
-          gradhyp[h] -= dot2(inv.data(), obssd_gradhyp.col(h), N);
+          gradhyp[h] += dot_seq(residtemp2.data(), obssd_gradhyp.col(h), N);
+          gradhyp[h] -= dot_seq(inv.data(), obssd_gradhyp.col(h), N);
         }
       }
     }
     if (compute_gradpara) {
       gradpara.assign(2, 0.0);
       for (u64 c = 0; c < 2; ++c) {
-        gradpara[c] = dot2(residtemp2.data(), obssd_gradpara.col(c), N);
-        gradpara[c] -= dot2(inv.data(), obssd_gradpara.col(c), N);
+        gradpara[c] = dot_seq(residtemp2.data(), obssd_gradpara.col(c), N);
+        gradpara[c] -= dot_seq(inv.data(), obssd_gradpara.col(c), N);
       }
     }
   }
@@ -1582,3 +1595,14 @@ vec pred_gauss::var() const { /* :223-227 */
 }
 
 } // namespace orc
+
+/* The eigen-solver above, exported for oracle/ref_capi.cpp: the reference build (unmodified sources + Armadillo shim)
+ * routes eig_sym to the SAME routine, so that both sides share one eigenbasis (SURVEY 7 "hard parts", 8c). */
+extern "C" void orc_eig_sym_jacobi(uint64_t n, const double* A, double* w, double* V) {
+  orc::mat Ain(n, n), Vm;
+  std::copy(A, A + n * n, Ain.a.begin());
+  orc::vec wv;
+  orc::eig_sym_jacobi(wv, Vm, Ain);
+  std::copy(wv.begin(), wv.end(), w);
+  std::copy(Vm.a.begin(), Vm.a.end(), V);
+}

@@ -6,17 +6,17 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this.  The product (outerbase_b200/) never does.
  *
- * PARITY PINNING: the reference ships no golden vectors (its tests pin
- * identities only -- SURVEY 8c) and cannot be built here (no R/Rcpp/Armadillo/
- * LAPACK headers), so this oracle is pinned by (i) the reference's own test
- * identities restated in tests/test_oracle_*.py at the reference's shapes,
- * (ii) an independent numpy/scipy restatement (scipy.linalg.eigh = LAPACK) of
- * the eigenbasis and covariance formulas, and (iii) committed golden fixtures
- * generated from it (tests/golden/).  Third-party arithmetic the reference
- * delegates to unpinned RcppArmadillo / R BLAS+LAPACK (eig_sym, dgemm, ddot,
- * R's RNG in shuffle) is restated as: cyclic Jacobi eigensolver, k-ascending
- * triple loop, Armadillo's two-accumulator sum/dot, injectable tie-break.
- * => "parity unpinned" at that third-party boundary; pinned everywhere else.
+ * PARITY PINNING: **pinned against the reference itself** (round 2).  `make -C oracle ref` compiles the UNMODIFIED
+ * reference sources (/root/reference/src/{linalg,covfuncs,modandbase,fit}.cpp + lpdfs/) against oracle/arma_shim (a
+ * header-only Armadillo subset) into oracle/_ref/libob_ref.so; tests/test_oracle_ref.py holds this oracle BITWISE equal
+ * to it with one OpenMP thread -- terms, index tables, eigenbasis, basis matrices, every linalg.h kernel on both vertpl
+ * branches, loglik_gauss / logpr_gauss / lpdfvec / loglik_gda, optcg iterates, a whole BFGS_lpdf run -- and to rounding
+ * (<= 1e-13) with several threads, where the reference itself adds thread-local sums in arrival order.  The reference
+ * ships no golden vectors of its own; committed fixtures (tests/golden/) freeze these outputs.
+ * Still third-party, and SHARED by both sides of that comparison rather than pinned: eig_sym (LAPACK upstream; cyclic
+ * Jacobi here), the BLAS behind Armadillo (netlib reference order here: dot_seq / k-ascending gemm) and R's RNG in
+ * shuffle (injectable tie-break).  tests/test_oracle_ref.py::test_blas_flavour_sensitivity shows what the BLAS choice
+ * moves (nothing in the linalg.h kernels on shared inputs; the high levels of the basis build).
  *
  * Each function cites the reference file:line it follows (paths relative to
  * the reference tree, src/...).
@@ -65,6 +65,9 @@ struct umat {
  * even/odd interleave, acc1 + acc2 at the end (call sites src/linalg.cpp:293,374,382). */
 double accu2(const double* x, u64 n);
 double dot2(const double* x, const double* y, u64 n);
+/* netlib ddot / dgemv('T') order (left to right), and Armadillo's dot() = dot2 up to 32 elements, BLAS above */
+double dot_seq(const double* x, const double* y, u64 n);
+double dot_arma(const double* x, const double* y, u64 n);
 
 /* ---- covariance functions: src/covfuncs.h:4-69, src/covfuncs.cpp:35-347 ---- */
 struct covf {
