@@ -184,11 +184,11 @@ struct SpecKernels {
 
 obs::SpecOptions spec_default_options() {
   obs::SpecOptions o;
-  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc,qd,tgd,cache_d,maxcols_d -- tuning only */
+  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc,qd,tgd,cache_d,maxcols_d,nreg_c,nreg_p,psleep -- tuning only */
     int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut, &o.mw, &o.kc,
-                &o.qd, &o.tgd, &o.cache_d, &o.maxcols_d};
+                &o.qd, &o.tgd, &o.cache_d, &o.maxcols_d, &o.nreg_c, &o.nreg_p, &o.psleep};
     int i = 0;
-    for (const char* p = e; *p && i < 18; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (const char* p = e; *p && i < 21; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
   }
   return o;
 }
@@ -319,7 +319,8 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   const int K = (int)pr.host.K;
   if (K == 0) return;
   if (pl.N == 0) { launch_fill(c, out, K, 0.0); return; }
-  if (pl.cols->nload != pl.cols->ncol) throw std::logic_error("specialised kernels take plain column tables only");
+  if (pl.cols->nload != pl.cols->ncol || pl.cols->has_ops) throw std::logic_error("specialised Phi^T takes stored columns only (no per-column ops)");
+  if (pl.N >= (1ull << 31)) throw std::range_error("specialised Phi^T: more than 2^31 - 1 rows per GPU");
   const int TR = k.tr_t;
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
@@ -465,7 +466,7 @@ bool launch_phi_d_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
     k.smem_d_set = smem;
   }
   void* args[] = {&p, &q};
-  const cudaError_t e = cudaLaunchKernel((const void*)k.kd, dim3(grid), dim3(32 * (warps + k.opt.np)), args, smem, c.stream);
+  const cudaError_t e = cudaLaunchKernel((const void*)k.kd, dim3(grid), dim3(32 * (warps + k.opt.npd)), args, smem, c.stream);
   if (e != cudaSuccess) throw CudaError(std::string("phi_d_spec: ") + cudaGetErrorString(e));
   c.launches++;
   sum_rows_kernel<<<(g.H + 63) / 64, 64, 0, c.stream>>>(q.partial, g.H, grid, out);
