@@ -103,6 +103,15 @@ struct Ctx {
   };
   void p2p_init();  /* after the NCCL communicator exists; leaves p2p.G == 0 when peer memory cannot be mapped */
   void p2p_release();
+  /* one call of the peer-memory protocol issued from another kernel (the fused tail of phi_t_spec): the slot blocks of
+   * all ranks and the next sequence number */
+  struct P2PCall { void* slots[P2P::kMaxRanks]; int G, rank; unsigned seq; unsigned long long timeout_ns; };
+  P2PCall p2p_next_call();
+  /* grid barrier of kernels that reduce in their own tail: a monotonic arrival counter, `sync_count` = arrivals
+   * requested so far (the target a launch waits for) */
+  unsigned* sync_ctr = nullptr;
+  unsigned sync_count = 0;
+  unsigned* grid_sync_counter();
 };
 
 /* device buffer, grows on demand, never shrinks */

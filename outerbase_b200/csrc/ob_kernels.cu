@@ -906,6 +906,7 @@ Ctx::Ctx(int dev) : device(dev) {
 Ctx::~Ctx() {
   p2p_release();
   if (comm && NcclApi::get().CommDestroy) NcclApi::get().CommDestroy(comm);
+  if (sync_ctr) cudaFree(sync_ctr);
   if (pinned) cudaFreeHost(pinned);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -1059,6 +1060,23 @@ static void p2p_launch(Ctx& c, double* buf, size_t n, const double* partial, int
 }
 
 bool Ctx::p2p_ok(size_t n) const { return p2p.G && p2p.enabled && n <= P2P::kCap; }
+
+Ctx::P2PCall Ctx::p2p_next_call() {
+  P2PCall a{};
+  for (int r = 0; r < p2p.G; ++r) a.slots[r] = p2p.peer[r];
+  if (++p2p.seq == 0) p2p.seq = 2; /* as p2p_launch: 0 is the tag of the zero-initialised buffer */
+  a.G = p2p.G; a.rank = rank; a.seq = p2p.seq; a.timeout_ns = p2p.timeout_ns;
+  return a;
+}
+
+unsigned* Ctx::grid_sync_counter() {
+  if (!sync_ctr) {
+    OB_CUDA(cudaMalloc(&sync_ctr, sizeof(unsigned)));
+    OB_CUDA(cudaMemsetAsync(sync_ctr, 0, sizeof(unsigned), stream));
+    sync_count = 0;
+  }
+  return sync_ctr;
+}
 
 void Ctx::allreduce_sum(double* buf, size_t n) {
   if (nranks <= 1 || !comm || n == 0) return;

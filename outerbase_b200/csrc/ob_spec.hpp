@@ -45,6 +45,12 @@ struct SpecParams {
   unsigned long long N;
   int ncol, has_ops, sq, mode, ntiles, nstage, nslots;
   unsigned off_tile, tile_doubles, off_vec, off_flags;
+  /* Phi^T: cross-CTA (and cross-GPU) reduction in the tail of the same launch (fuse_tail != 0) */
+  unsigned* sync_ctr;            /* monotonic arrival counter of the context (grid barrier) */
+  void* peer[8];                 /* the peer-memory slot block of every rank (Ctx::P2P), G > 1 */
+  unsigned long long timeout_ns;
+  unsigned sync_target, seq;
+  int G, rank, fuse_tail, pad_;
 };
 
 /* mirrored by `struct MatParams` in ob_spec_scaffold.inc (phi_am_spec) */

@@ -163,6 +163,7 @@ struct SpecKernels {
   size_t vec_bytes_a = 0; /* shared-memory copy of the coefficients, slot order */
   size_t smem_a_set = 0, smem_t_set = 0;
   int max_clusters = 0;
+  bool fuse_ok = true; /* phi_t_spec may reduce in its own tail (cooperative launch accepted so far) */
   /* multi right-hand-side module (phi_am_spec), built at first use */
   cudaLibrary_t libm = nullptr;
   cudaKernel_t km = nullptr;
@@ -235,6 +236,17 @@ static void spec_fill(obs::SpecParams& p, const PhiPlan& pl, int TR) {
   p.scale = pl.scale; p.sq = pl.sq; p.N = pl.N;
   p.ncol = pl.cols->ncol; p.has_ops = pl.cols->has_ops ? 1 : 0;
   p.ntiles = (int)((pl.N + TR - 1) / TR);
+}
+
+static cudaError_t spec_launch_try(Ctx& c, cudaKernel_t kern, int grid, int threads, size_t smem, obs::SpecParams& p, bool cooperative) {
+  void* args[] = {&p};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = c.stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeCooperative;
+  at.val.cooperative = 1;
+  cfg.attrs = &at; cfg.numAttrs = cooperative ? 1 : 0;
+  return cudaLaunchKernelExC(&cfg, (const void*)kern, args);
 }
 
 static void spec_launch(Ctx& c, cudaKernel_t kern, size_t& smem_set, int grid, int threads, size_t smem, obs::SpecParams& p, const char* what,
@@ -352,6 +364,38 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   p.win = w;
   p.nslots = (int)pr.host.nslots();
   p.partial = ws.partial.ensure((size_t)J * p.nslots);
+  /* The cross-CTA sum (and, when the caller's allreduce rides along, the cross-GPU sum) runs in the tail of the same
+   * launch: needs every CTA resident at once, which a cooperative launch guarantees.  OB_FUSE_TAIL=0 or a refused
+   * cooperative launch (SMs held by somebody else) fall back to the separate reduction kernel. */
+  static const bool fuse_env = !(getenv("OB_FUSE_TAIL") && std::string(getenv("OB_FUSE_TAIL")) == "0");
+  if (fuse_env && k.cluster == 1 && k.fuse_ok && grid <= c.sms) {
+    const bool ranks = c.fuse_n == (size_t)K && c.p2p_ok((size_t)K);
+    if (g.smem > k.smem_t_set) {
+      OB_CUDA(cudaFuncSetAttribute((const void*)k.kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+      k.smem_t_set = g.smem;
+    }
+    p.out = out; p.slot_term = pr.slot_term.p;
+    p.sync_ctr = c.grid_sync_counter();
+    p.sync_target = c.sync_count + (unsigned)grid;
+    p.fuse_tail = 1; p.G = 1; p.rank = 0; p.seq = 0;
+    Ctx::P2PCall call{};
+    if (ranks) {
+      call = c.p2p_next_call();
+      for (int r = 0; r < call.G; ++r) p.peer[r] = call.slots[r];
+      p.G = call.G; p.rank = call.rank; p.seq = call.seq; p.timeout_ns = call.timeout_ns;
+    }
+    const cudaError_t e = spec_launch_try(c, k.kt, grid, 32 * (k.opt.wt + k.opt.np), g.smem, p, /*cooperative=*/true);
+    if (e == cudaSuccess) {
+      c.sync_count += (unsigned)grid;
+      c.launches++;
+      if (ranks) { c.fuse_n = 0; c.fused = true; }
+      return;
+    }
+    (void)cudaGetLastError();
+    if (ranks) throw CudaError(std::string("phi_t_spec (fused tail): ") + cudaGetErrorString(e)); /* the sequence number is spent */
+    k.fuse_ok = false; /* this GPU cannot hold the grid at once (shared with other work): separate reduction from now on */
+    p.fuse_tail = 0;
+  }
   spec_launch(c, k.kt, k.smem_t_set, grid, 32 * (k.opt.wt + k.opt.np), g.smem, p, "phi_t_spec", k.cluster);
   launch_phi_t_reduce(c, p.partial, J, p.nslots, pr.slot_term.p, out);
 }

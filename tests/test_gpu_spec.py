@@ -30,7 +30,7 @@ def test_spec_seam_matvecs_on_oracle_basis(spec, oracle, N, K):
     n0 = spec.launch_count()
     assert relerr(spec.prodmm(terms, a, o["bm"], o["bs"], o["kp"]), o["ob"].matmul(terms, a)) < MATVEC_TOL
     assert relerr(spec.tprodmm(terms, r, o["bm"], o["bs"], o["kp"]), o["ob"].tmatmul(terms, r)) < MATVEC_TOL
-    assert spec.launch_count() >= n0 + 3  # phi_a_spec, phi_t_spec, reduce
+    assert spec.launch_count() >= n0 + 2  # phi_a_spec, phi_t_spec (the cross-CTA reduction runs in its tail)
 
 
 @pytest.mark.parametrize("N", [1, 31, 127, 128, 129, 255, 256, 257, 1000])
