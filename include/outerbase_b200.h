@@ -186,7 +186,9 @@ int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uin
  * src/linalg.cpp:139-163, 225-277; loglik_gauss.cpp:127; fit.cpp:259-263) from ONE reverse-mode
  * sweep over the rows (kernel phi_d_spec) instead of one product per hyper-parameter.  dsweep is
  * on by default (same value on every rank; a rank whose module fails to build makes all ranks fall
- * back to the per-hyper products together). */
+ * back to the per-hyper products together); "device_cg" 1|0 (env OB_DEVICE_CG) -- lpdf::optcg
+ * (src/fit.cpp:37-96) on lpdfvec(logpr_gauss, loglik_gauss) keeps every K-vector and scalar of the
+ * loop in HBM (the host reads one stop flag per iteration); 0 = the host loop of round 1. */
 int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
 int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
 /* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */

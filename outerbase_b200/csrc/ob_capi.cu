@@ -252,6 +252,7 @@ int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value) {
     ctx->c.spec_mode = (int)value;
   } else if (n == "spec_work") ctx->c.spec_work = value;
   else if (n == "dsweep") ctx->c.dsweep = value != 0;
+  else if (n == "device_cg") ctx->c.device_cg = value != 0;
   else if (n == "p2p") ctx->c.p2p.enabled = value != 0; /* same value on every rank */
   else throw std::invalid_argument("unknown option " + n);
   OB_CATCH

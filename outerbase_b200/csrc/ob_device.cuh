@@ -90,6 +90,14 @@ struct Ctx {
    * allreduce when the product did not end in that kernel (rows == 0, brute-force kernels). */
   size_t fuse_n = 0;
   bool fused = false;
+  /* one more element rides on a fused Phi^T tail: the fixed-order sum of `fuse_extra_n` doubles (the per-CTA sums of
+   * squared residuals of the preceding Phi a launch, loglik_gauss.cpp:122) lands in out[K]; extra_done tells the
+   * caller whether the launch took care of it */
+  const double* fuse_extra = nullptr;
+  int fuse_extra_n = 0;
+  bool extra_done = false;
+  /* lpdf::optcg with every K-vector in HBM (option "device_cg", env OB_DEVICE_CG; on by default) */
+  bool device_cg = true;
   void fuse_allreduce(size_t n) { fused = false; fuse_n = p2p_ok(n) ? n : 0; }
   void allreduce_after(double* buf_dev, size_t n) {
     fuse_n = 0;
@@ -98,8 +106,11 @@ struct Ctx {
   }
   struct FuseScope { /* exception-safe request: a product that throws must not leave the request armed */
     Ctx& c;
-    FuseScope(Ctx& c_, size_t n) : c(c_) { c.fuse_allreduce(n); }
-    ~FuseScope() { c.fuse_n = 0; }
+    FuseScope(Ctx& c_, size_t n, const double* extra = nullptr, int extra_n = 0) : c(c_) {
+      c.fuse_allreduce(n);
+      c.fuse_extra = extra; c.fuse_extra_n = extra ? extra_n : 0; c.extra_done = false;
+    }
+    ~FuseScope() { c.fuse_n = 0; c.fuse_extra = nullptr; c.fuse_extra_n = 0; }
   };
   void p2p_init();  /* after the NCCL communicator exists; leaves p2p.G == 0 when peer memory cannot be mapped */
   void p2p_release();
@@ -112,6 +123,23 @@ struct Ctx {
   unsigned* sync_ctr = nullptr;
   unsigned sync_count = 0;
   unsigned* grid_sync_counter();
+  /* Host-pointer calls of the reference's interface (outerbase::tmm with a host vector) overlap the host -> device copy
+   * with the kernel that consumes it: the copy runs in chunks on `copy_stream`, each followed by a 4-byte copy that
+   * publishes the rows that have arrived in `rows_ready`; the Phi^T producers poll it before staging a tile.
+   *   stream_rows_begin()        (main stream) reset the counter, returns its device address
+   *   ... launch the consumer on the main stream ...
+   *   stream_rows_copy(dst, src, n)   issue the chunked copy (after the launch: a pageable source blocks the host)
+   *   stream_rows_end()          main stream waits for the copy */
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
+  unsigned* rows_ready = nullptr;
+  unsigned* rows_table = nullptr; /* pinned: the values published after each chunk */
+  const unsigned* stream_rows_begin();
+  void stream_rows_copy(double* dst_dev, const double* src_host, size_t n);
+  void stream_rows_end();
+  /* device address of a caller's host buffer when it is page-locked and mapped (kernels then write results straight
+   * into it, overlapping the device -> host transfer with the computation), else null */
+  static double* mapped_host_pointer(double* host);
 };
 
 /* device buffer, grows on demand, never shrinks */
@@ -215,7 +243,7 @@ bool spec_uses_cluster(const SpecKernels& k);
 /* true when [p, p + bytes) lies inside one device allocation (cuMemGetAddressRange through the runtime's driver entry point) */
 bool device_range_readable(const void* p, size_t bytes);
 void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
-void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws);
+void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws, const unsigned* ready = nullptr);
 /* Phi . A on the FP64 tensor cores (phi_am_spec): A is K x C column-major (device), out N x C with leading dimension ldo.
  * The module is generated and compiled at first use.  Returns false when the tile does not fit (caller: column loop). */
 /* model-side tables of the hyper-gradient sweep (phi_d_spec): where the gradient columns of each hyper-parameter live */
@@ -236,6 +264,28 @@ void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int nco
 void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo);
 /* sum of n per-CTA partials, fixed order -> out[0] */
 void launch_sum_partials(Ctx& c, const double* partial, int n, double* out);
+
+/* ---- device-resident CG (lpdf::optcg, src/fit.cpp:37-96, on lpdfvec(logpr_gauss, loglik_gauss) in either order): the
+ * K-vector algebra of one iteration between the Phi kernels, ONE single-CTA launch per stage, every vector and scalar
+ * in HBM, so that an iteration never waits for the host.  Sums use one fixed tree order (deterministic; the reference's
+ * two-accumulator `accu` order is sequential and would cost ~8 us per sum on one thread -- the iterates differ by
+ * rounding, inside the 1e-8 budget of the fit). */
+enum CgStage : int {
+  CG_INIT = 0,              /* after the first update() (host path): rm = grad / m ; p = rm                         (:58-60)  */
+  CG_FINISH_Q = 1,          /* q = hessmult(p) = lik part + p / (sd sca)^2 in child order                          (:59)     */
+  CG_STEP = 2,              /* q as above; num = grad.rm ; stop test ; denom = q.p ; alpha ; coeff += alpha p ; valo (:72-77) */
+  CG_POST_UPDATE = 3        /* grad, val ; valdiff ; rm ; num2 = -(alpha q).rm ; beta ; p = rm + beta p             (:79-83) */
+};
+struct CgParams {
+  int K, stage, lik_first, domarg;
+  double* coeff; double* grad; const double* m; double* rm; double* p; double* q;
+  const double* red;    /* K + 1: likelihood part of grad (update) or of the Hessian product (hessmult) | sum of squared residuals */
+  const double* sds;    /* K: coeffsd (logpr_gauss.cpp:57) */
+  double sca, obssd, nglobal, val_margadj, tol;
+  double* scal;         /* [0] num [1] denom [2] alpha [3] beta [4] val [5] valo [6] valdiff [7] stop [8] val_lik [9] val_pr */
+};
+enum { CG_NUM = 0, CG_DENOM, CG_ALPHA, CG_BETA, CG_VAL, CG_VALO, CG_VALDIFF, CG_STOP, CG_VAL_LIK, CG_VAL_PR, CG_NSCAL = 16 };
+void launch_cg_stage(Ctx& c, const CgParams& p);
 
 /* basis build: cov(x, knots) . rotmat, normalise (modandbase.cpp:285-327, 547-626) */
 struct BuildDims {

@@ -272,7 +272,9 @@ struct OuterBase {
    * (w_rows < ld) is used in place when the device allocation it lives in extends that far (the driver tells), and
    * copied to a padded buffer otherwise. */
   DevBuf<double> tmpW;
-  void phi_t(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, u64 w_rows = ~(u64)0) {
+  /* `ready`: the input vector is still being copied in (Ctx::stream_rows_*); only the specialised kernel can consume
+   * it that way -- returns false, having launched nothing, when the table is not specialised */
+  bool phi_t(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, u64 w_rows = ~(u64)0, const unsigned* ready = nullptr) {
     if (SpecEntry* e = spec_for(terms, K)) {
       const bool misaligned = reinterpret_cast<uintptr_t>(w_dev) & 15u;
       if (misaligned || (w_rows < ld && N % 256 != 0 && !obd::device_range_readable(w_dev, ld * sizeof(double)))) {
@@ -280,10 +282,12 @@ struct OuterBase {
         OB_CUDA(cudaMemcpyAsync(tmpW.p, w_dev, N * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
         w_dev = tmpW.p;
       }
-      obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), w_dev, out_dev, ws);
-      return;
+      obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), w_dev, out_dev, ws, obd::spec_uses_cluster(*e->k) ? nullptr : ready);
+      return !ready || !obd::spec_uses_cluster(*e->k);
     }
+    if (ready) return false;
     obd::launch_phi_t(ctx, plan(program(terms, K, -1, 1), sq, -1), w_dev, out_dev, ws);
+    return true;
   }
 
   /* gradhyp[h] = sum_n w_n * outge[n,h] for every hyper-parameter, outge = prodmmge_ (linalg.cpp:225-277), in the
@@ -405,11 +409,13 @@ struct OuterBase {
     obd::PhiAArgs a; a.a = a_dev; a.out = out_dev; a.mode = obd::PHI_PLAIN;
     phi_a(terms, K, sq, a, nullptr);
   }
-  void tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true, u64 w_rows = ~(u64)0) {
-    if (!reduce_ranks) { phi_t(terms, K, sq, w_dev, out_dev, w_rows); return; }
+  bool tmm_dev(const u64* terms, u64 K, int sq, const double* w_dev, double* out_dev, bool reduce_ranks = true, u64 w_rows = ~(u64)0,
+               const unsigned* ready = nullptr) {
+    if (!reduce_ranks) return phi_t(terms, K, sq, w_dev, out_dev, w_rows, ready);
     obd::Ctx::FuseScope fuse(ctx, K); /* cross-CTA and cross-rank reductions in one launch when peer memory is mapped */
-    phi_t(terms, K, sq, w_dev, out_dev, w_rows);
+    if (!phi_t(terms, K, sq, w_dev, out_dev, w_rows, ready)) return false;
     ctx.allreduce_after(out_dev, K);
+    return true;
   }
   /* prodmmge_: outge column h = augmented-program product (ob_terms.hpp) */
   void mm_ge_dev(const u64* terms, u64 K, int sq, const double* a_dev, double* out_dev, double* outge_dev, u64 ldo) {
@@ -484,17 +490,36 @@ struct OuterBase {
     if (n) OB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
   }
+  /* The host-pointer forms overlap their transfers with the kernel (bench.py's `e2e`): a page-locked, mapped result
+   * buffer is written by the kernel itself while it computes; an input vector is copied in chunks on a second stream
+   * while the Phi^T kernel already consumes the rows that have arrived. */
+  static constexpr u64 kOverlapRows = 1u << 17;
   void mm(int sq, const u64* terms, u64 K, const double* a, double* out) {
     tmpK.upload(a, K, ctx.stream);
+    if (N >= kOverlapRows)
+      if (double* mapped = obd::Ctx::mapped_host_pointer(out)) {
+        mm_dev(terms, K, sq, tmpK.p, mapped);
+        ctx.sync();
+        return;
+      }
     tmpN.ensure(ld);
     mm_dev(terms, K, sq, tmpK.p, tmpN.p);
     d2h(out, tmpN.p, N);
   }
   void tmm(int sq, const u64* terms, u64 K, const double* a, double* out) {
     tmpN.ensure(ld);
-    if (N) OB_CUDA(cudaMemcpyAsync(tmpN.p, a, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
     tmpK.ensure(K);
-    tmm_dev(terms, K, sq, tmpN.p, tmpK.p);
+    bool done = false;
+    if (N >= kOverlapRows && N < (1ull << 31)) {
+      const unsigned* ready = ctx.stream_rows_begin();
+      done = tmm_dev(terms, K, sq, tmpN.p, tmpK.p, true, ~(u64)0, ready);
+      if (done) ctx.stream_rows_copy(tmpN.p, a, N); /* after the launch: a pageable source blocks the host per chunk */
+      ctx.stream_rows_end();
+    }
+    if (!done) {
+      if (N) OB_CUDA(cudaMemcpyAsync(tmpN.p, a, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+      tmm_dev(terms, K, sq, tmpN.p, tmpK.p);
+    }
     d2h(out, tmpK.p, K);
   }
   void mm_gradhyp(int sq, const u64* terms, u64 K, const double* a, double* out, double* outge) {
@@ -860,6 +885,39 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
     ob.d2h(o.data(), red.p, K);
     return o;
   }
+  /* ---- device forms for the HBM-resident CG (LpdfVec::optcg_device): coefficient vector in, likelihood part of the
+   * result in red[0..K) (summed over ranks), nothing crosses to the host.  update: red[K] = sum of squared
+   * standardised residuals, riding on the tail of the Phi^T launch (loglik_gauss.cpp:110-125). */
+  void update_dev(const double* coeff_dev) {
+    const u64 K = nterms;
+    obd::PhiAArgs a;
+    a.a = coeff_dev; a.out = yhat.p; a.w = w.p; a.y = y.p; a.sd = obssd; a.mode = obd::PHI_UPDATE;
+    int grid = 0;
+    ob.phi_a(terms.data(), K, 0, a, &grid);
+    yhat_valid = false;
+    red.ensure(K + 2);
+    bool fused;
+    {
+      obd::Ctx::FuseScope fuse(ctx, K + 1, ob.ws.ssq.p, grid);
+      ob.phi_t(terms.data(), K, 0, w.p, red.p);
+      fused = ctx.fused; ctx.fused = false;
+    }
+    if (!ctx.extra_done) {
+      if (grid > 0) obd::launch_sum_partials(ctx, ob.ws.ssq.p, grid, red.p + K);
+      else OB_CUDA(cudaMemsetAsync(red.p + K, 0, sizeof(double), ctx.stream));
+    }
+    if (!fused) ctx.allreduce_sum(red.p, K + 1);
+  }
+  void hessmult_dev(const double* g_dev) { /* :137-145 */
+    const u64 K = nterms;
+    obd::PhiAArgs a;
+    a.a = g_dev; a.w = w.p; a.sd = obssd; a.mode = obd::PHI_HESS;
+    ob.phi_a(terms.data(), K, 0, a, nullptr);
+    red.ensure(K + 2);
+    obd::Ctx::FuseScope fuse(ctx, K);
+    ob.phi_t(terms.data(), K, 0, w.p, red.p);
+    ctx.allreduce_after(red.p, K);
+  }
   const double* ones_dev() {
     if (ones.cap < ob.ld) { ones.ensure(ob.ld); obd::launch_fill(ctx, ones.p, ob.ld, 1.0); }
     return ones.p;
@@ -1189,6 +1247,64 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
     std::vector<double> out = kid[0]->hessmult(g), h = kid[1]->hessmult(g);
     for (u64 i = 0; i < out.size(); ++i) out[i] += h[i];
     return out;
+  }
+  /* lpdf::optcg (fit.cpp:37-96) with every K-vector and scalar of the loop in HBM: for lpdfvec(logpr_gauss,
+   * loglik_gauss) in either order on a specialised terms table.  The reference's sequence is kept operation by
+   * operation -- first update() and diaghess() through the host path (they build the cached Hessian diagonal and the
+   * marginal adjustment, fit.cpp:252-267), then per iteration: CG_STEP | stop test | update | CG_POST_UPDATE | hessmult,
+   * each a few launches on the library stream; the host reads ONE double per iteration (the stop flag); the final
+   * update() with gradients runs through the host path again.  Falls back (returns false) for every other pairing. */
+  DevBuf<double> cg_coeff, cg_grad, cg_m, cg_rm, cg_p, cg_q, cg_sds, cg_scal;
+  bool optcg_device(double tol, u64 maxepch) {
+    LoglikGauss* lk = dynamic_cast<LoglikGauss*>(kid[0]);
+    LogprGauss* pr = dynamic_cast<LogprGauss*>(kid[1]);
+    const bool lik_first = lk && pr;
+    if (!lik_first) { lk = dynamic_cast<LoglikGauss*>(kid[1]); pr = dynamic_cast<LogprGauss*>(kid[0]); }
+    if (!lk || !pr) return false;
+    Ctx& ctx = lk->ctx;
+    const u64 K = nterms;
+    if (!ctx.device_cg || K == 0 || lk->N == 0 || !lk->ob.spec_for(terms.data(), K)) return false;
+    compute_val = true; compute_grad = true; compute_gradhyp = false; compute_gradpara = false;
+    if (coeff.size() != nterms) coeff.assign(nterms, 0.0);
+    update(std::vector<double>(coeff));
+    std::vector<double> m = diaghess();
+    cg_iters = 0;
+    if (!all_finite(m) && !all_finite(grad)) { val = -std::numeric_limits<double>::infinity(); return true; }
+    cg_coeff.upload(coeff, ctx.stream); cg_grad.upload(grad, ctx.stream); cg_m.upload(m, ctx.stream);
+    cg_sds.upload(pr->coeffsd, ctx.stream);
+    cg_rm.ensure(K); cg_p.ensure(K); cg_q.ensure(K);
+    std::vector<double> scal(obd::CG_NSCAL, 0.0);
+    scal[obd::CG_VAL] = val; scal[obd::CG_VALO] = val; scal[obd::CG_VALDIFF] = 10; scal[obd::CG_DENOM] = 1;
+    cg_scal.upload(scal, ctx.stream);
+    ctx.sync(); /* the host images above must outlive the uploads */
+    obd::CgParams c{};
+    c.K = (int)K; c.lik_first = lik_first ? 1 : 0; c.domarg = domargadj ? 1 : 0;
+    c.coeff = cg_coeff.p; c.grad = cg_grad.p; c.m = cg_m.p; c.rm = cg_rm.p; c.p = cg_p.p; c.q = cg_q.p; c.sds = cg_sds.p;
+    c.sca = pr->sca; c.obssd = lk->obssd; c.nglobal = lk->Nglobal; c.val_margadj = val_margadj; c.tol = tol; c.scal = cg_scal.p;
+    auto stage = [&](int st) { c.stage = st; c.red = lk->red.p; obd::launch_cg_stage(ctx, c); };
+    lk->red.ensure(K + 2);
+    stage(obd::CG_INIT);          /* rm = grad / m ; p = rm                       :58-60 */
+    lk->hessmult_dev(cg_p.p);     /* q = hessmult(p), finished inside CG_STEP     :62 */
+    u64 k;
+    for (k = 0; k < maxepch; k++) {
+      stage(obd::CG_STEP);        /* q ; num ; stop test ; denom ; alpha ; coeff += alpha p ; valo   :72-77 */
+      OB_CUDA(cudaMemcpyAsync(ctx.pinned, cg_scal.p + obd::CG_STOP, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      if (ctx.pinned[0] != 0.0) break;
+      lk->update_dev(cg_coeff.p); /* update(coeff)                                :78 */
+      stage(obd::CG_POST_UPDATE); /* grad ; val ; valdiff ; rm ; beta ; p         :79-83 */
+      lk->hessmult_dev(cg_p.p);   /* q = hessmult(p)                              :84 */
+    }
+    cg_iters = k;
+    OB_CUDA(cudaMemcpyAsync(coeff.data(), cg_coeff.p, K * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    compute_gradhyp = true; compute_gradpara = true;
+    update(std::vector<double>(coeff));
+    compute_gradhyp = false; compute_gradpara = false;
+    return true;
+  }
+  void optcg(double tol, u64 maxepch) override {
+    if (!optcg_device(tol, maxepch)) Lpdf::optcg(tol, maxepch);
   }
   std::vector<double> diaghess() override { return diaghessv; }
   std::vector<double> diaghessgradhyp() override {

@@ -897,6 +897,7 @@ Ctx::Ctx(int dev) : device(dev) {
   OB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   OB_CUDA(cudaMallocHost(&pinned, 4096 * sizeof(double)));
   if (const char* e = getenv("OB_DSWEEP")) dsweep = std::string(e) != "0";
+  if (const char* e = getenv("OB_DEVICE_CG")) device_cg = std::string(e) != "0";
   if (const char* e = getenv("OB_SPEC")) { /* 0 | 1 | auto */
     const std::string v(e);
     spec_mode = v == "0" ? 0 : (v == "1" ? 1 : 2);
@@ -907,6 +908,11 @@ Ctx::~Ctx() {
   p2p_release();
   if (comm && NcclApi::get().CommDestroy) NcclApi::get().CommDestroy(comm);
   if (sync_ctr) cudaFree(sync_ctr);
+  if (rows_ready) cudaFree(rows_ready);
+  if (rows_table) cudaFreeHost(rows_table);
+  if (ev_main) cudaEventDestroy(ev_main);
+  if (ev_copy) cudaEventDestroy(ev_copy);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (pinned) cudaFreeHost(pinned);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -1067,6 +1073,42 @@ Ctx::P2PCall Ctx::p2p_next_call() {
   if (++p2p.seq == 0) p2p.seq = 2; /* as p2p_launch: 0 is the tag of the zero-initialised buffer */
   a.G = p2p.G; a.rank = rank; a.seq = p2p.seq; a.timeout_ns = p2p.timeout_ns;
   return a;
+}
+
+const unsigned* Ctx::stream_rows_begin() {
+  if (!copy_stream) {
+    OB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    OB_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+    OB_CUDA(cudaMalloc(&rows_ready, sizeof(unsigned)));
+    OB_CUDA(cudaMallocHost(&rows_table, 64 * sizeof(unsigned)));
+  }
+  OB_CUDA(cudaMemsetAsync(rows_ready, 0, sizeof(unsigned), stream));
+  OB_CUDA(cudaEventRecord(ev_main, stream));
+  OB_CUDA(cudaStreamWaitEvent(copy_stream, ev_main, 0));
+  return rows_ready;
+}
+
+void Ctx::stream_rows_copy(double* dst, const double* src, size_t n) {
+  const size_t chunks = std::min<size_t>(16, std::max<size_t>(1, n / 65536));
+  const size_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;
+  size_t c = 0;
+  for (size_t r0 = 0; r0 < n; r0 += per, ++c) {
+    const size_t r1 = std::min(n, r0 + per);
+    OB_CUDA(cudaMemcpyAsync(dst + r0, src + r0, (r1 - r0) * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+    rows_table[c] = (unsigned)r1;
+    OB_CUDA(cudaMemcpyAsync(rows_ready, rows_table + c, sizeof(unsigned), cudaMemcpyHostToDevice, copy_stream));
+  }
+  OB_CUDA(cudaEventRecord(ev_copy, copy_stream));
+}
+
+void Ctx::stream_rows_end() { OB_CUDA(cudaStreamWaitEvent(stream, ev_copy, 0)); }
+
+double* Ctx::mapped_host_pointer(double* host) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return static_cast<double*>(at.devicePointer);
 }
 
 unsigned* Ctx::grid_sync_counter() {
@@ -1342,6 +1384,90 @@ void launch_getmat(Ctx& c, const PhiPlan& pl, double* out, u64 ldo) {
   getmat_kernel<<<grid, bs, 0, c.stream>>>(pl.cols->load_src.p, pl.cols->col_op.p, pr.csr_ptr.p, pr.csr_col.p, (int)pr.host.K,
                                           pl.scale, pl.sq, pl.N, out, ldo);
   check_launch(c, "getmat_kernel");
+}
+
+/* ------------------------------------------------------------------ device-resident CG stages (ob_device.cuh) */
+constexpr int kCgThreads = 1024;
+/* sum over the CTA in a fixed order: lanes by butterfly, warps in index order by thread 0; all threads get the result */
+__device__ double cg_block_sum(double v, double* sm) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  __syncthreads(); /* sm may still be read from the previous sum */
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kCgThreads / 32; ++w) s += sm[w];
+    sm[32] = s;
+  }
+  __syncthreads();
+  return sm[32];
+}
+
+__global__ void __launch_bounds__(kCgThreads) cg_stage_kernel(const CgParams c) {
+  __shared__ double sm[33];
+  const int K = c.K, tid = threadIdx.x;
+  double* S = c.scal;
+  if (c.stage == CG_INIT) {
+    for (int i = tid; i < K; i += kCgThreads) { const double rm = c.grad[i] / c.m[i]; c.rm[i] = rm; c.p[i] = rm; }
+    return;
+  }
+  if (c.stage == CG_POST_UPDATE) {
+    /* logpr_gauss::update (logpr_gauss.cpp:98-105) + loglik_gauss::update's scalars (loglik_gauss.cpp:121-128) +
+     * lpdfvec::update's sums over the children in their order (fit.cpp:352-361) */
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = tid; i < K; i += kCgThreads) {
+      const double sd = c.sds[i] * c.sca;
+      const double st = c.coeff[i] / sd;
+      s1 += st * st;
+      s2 += log(sd);
+      const double gpr = -1. * st / sd, glik = c.red[i];
+      c.grad[i] = c.lik_first ? (0.0 + glik) + gpr : (0.0 + gpr) + glik;
+    }
+    const double t1 = cg_block_sum(s1, sm), t2 = cg_block_sum(s2, sm);
+    const double val_pr = -0.5 * t1 - t2;
+    const double val_lik = -0.5 * c.red[K] - c.nglobal * log(c.obssd);
+    double val = c.lik_first ? (0.0 + val_lik) + val_pr : (0.0 + val_pr) + val_lik;
+    if (c.domarg) val += c.val_margadj;
+    const double valo = S[CG_VALO], alpha = S[CG_ALPHA], num = S[CG_NUM];
+    double s3 = 0.0;
+    for (int i = tid; i < K; i += kCgThreads) {
+      const double rm = c.grad[i] / c.m[i];
+      c.rm[i] = rm;
+      s3 += (alpha * c.q[i]) * rm;
+    }
+    const double num2 = -cg_block_sum(s3, sm);
+    const double beta = num2 / num;
+    for (int i = tid; i < K; i += kCgThreads) c.p[i] = c.rm[i] + beta * c.p[i];
+    if (tid == 0) { S[CG_BETA] = beta; S[CG_VALDIFF] = val - valo; S[CG_VAL] = val; S[CG_VAL_LIK] = val_lik; S[CG_VAL_PR] = val_pr; }
+    return;
+  }
+  /* q = hessmult(p): lpdfvec::hessmult sums the children in their order (fit.cpp:388-397); loglik part = red,
+   * logpr_gauss::hessmult = p / (sd sca)^2 (logpr_gauss.cpp:112-114) */
+  double sn = 0.0, sd_ = 0.0;
+  for (int i = tid; i < K; i += kCgThreads) {
+    const double sd = c.sds[i] * c.sca;
+    const double hp = c.p[i] / (sd * sd), hl = c.red[i];
+    const double q = c.lik_first ? hl + hp : hp + hl;
+    c.q[i] = q;
+    sn += c.grad[i] * c.rm[i];
+    sd_ += q * c.p[i];
+  }
+  if (c.stage == CG_FINISH_Q) return;
+  const double num = cg_block_sum(sn, sm), denom = cg_block_sum(sd_, sm);
+  const bool stop = num < c.tol && S[CG_VALDIFF] < c.tol; /* fit.cpp:73 */
+  const double alpha = num / denom;
+  if (!stop)
+    for (int i = tid; i < K; i += kCgThreads) c.coeff[i] += alpha * c.p[i];
+  if (tid == 0) {
+    S[CG_NUM] = num; S[CG_STOP] = stop ? 1.0 : 0.0;
+    if (!stop) { S[CG_DENOM] = denom; S[CG_ALPHA] = alpha; S[CG_VALO] = S[CG_VAL]; }
+  }
+}
+
+void launch_cg_stage(Ctx& c, const CgParams& p) {
+  cg_stage_kernel<<<1, kCgThreads, 0, c.stream>>>(p);
+  check_launch(c, "cg_stage_kernel");
 }
 
 void launch_sum_partials(Ctx& c, const double* partial, int n, double* out) {

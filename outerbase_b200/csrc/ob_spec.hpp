@@ -47,10 +47,13 @@ struct SpecParams {
   unsigned off_tile, tile_doubles, off_vec, off_flags;
   /* Phi^T: cross-CTA (and cross-GPU) reduction in the tail of the same launch (fuse_tail != 0) */
   unsigned* sync_ctr;            /* monotonic arrival counter of the context (grid barrier) */
+  const unsigned* ready;         /* Phi^T: rows of the input vector that have arrived so far (host -> device copy in
+                                    flight on another stream), or null: the whole vector is there */
+  const double* extra;           /* fused tail: element K of the result = fixed-order sum of extra[0..extra_n) */
   void* peer[8];                 /* the peer-memory slot block of every rank (Ctx::P2P), G > 1 */
   unsigned long long timeout_ns;
   unsigned sync_target, seq;
-  int G, rank, fuse_tail, pad_;
+  int G, rank, fuse_tail, extra_n;
 };
 
 /* mirrored by `struct MatParams` in ob_spec_scaffold.inc (phi_am_spec) */

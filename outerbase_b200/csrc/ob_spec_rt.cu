@@ -326,7 +326,7 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
   if (grid_out) *grid_out = grid;
 }
 
-void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws) {
+void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* w, double* out, Workspace& ws, const unsigned* ready) {
   const DevProgram& pr = *pl.prog;
   const int K = (int)pr.host.K;
   if (K == 0) return;
@@ -362,6 +362,8 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   const int J = std::max(1, std::min(p.ntiles, jmax));
   const int grid = J * k.types;
   p.win = w;
+  p.ready = k.cluster == 1 ? ready : nullptr;
+  if (ready && k.cluster != 1) throw std::logic_error("streamed input vector: not with the cluster variant");
   p.nslots = (int)pr.host.nslots();
   p.partial = ws.partial.ensure((size_t)J * p.nslots);
   /* The cross-CTA sum (and, when the caller's allreduce rides along, the cross-GPU sum) runs in the tail of the same
@@ -369,7 +371,9 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
    * cooperative launch (SMs held by somebody else) fall back to the separate reduction kernel. */
   static const bool fuse_env = !(getenv("OB_FUSE_TAIL") && std::string(getenv("OB_FUSE_TAIL")) == "0");
   if (fuse_env && k.cluster == 1 && k.fuse_ok && grid <= c.sms) {
-    const bool ranks = c.fuse_n == (size_t)K && c.p2p_ok((size_t)K);
+    const int nextra = c.fuse_extra && c.fuse_extra_n > 0 ? 1 : 0;
+    const bool ranks = c.fuse_n == (size_t)(K + nextra) && c.p2p_ok((size_t)(K + nextra));
+    p.extra = nextra ? c.fuse_extra : nullptr; p.extra_n = nextra ? c.fuse_extra_n : 0;
     if (g.smem > k.smem_t_set) {
       OB_CUDA(cudaFuncSetAttribute((const void*)k.kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
       k.smem_t_set = g.smem;
@@ -388,13 +392,14 @@ void launch_phi_t_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
     if (e == cudaSuccess) {
       c.sync_count += (unsigned)grid;
       c.launches++;
+      if (nextra) c.extra_done = true;
       if (ranks) { c.fuse_n = 0; c.fused = true; }
       return;
     }
     (void)cudaGetLastError();
     if (ranks) throw CudaError(std::string("phi_t_spec (fused tail): ") + cudaGetErrorString(e)); /* the sequence number is spent */
     k.fuse_ok = false; /* this GPU cannot hold the grid at once (shared with other work): separate reduction from now on */
-    p.fuse_tail = 0;
+    p.fuse_tail = 0; p.extra = nullptr; p.extra_n = 0;
   }
   spec_launch(c, k.kt, k.smem_t_set, grid, 32 * (k.opt.wt + k.opt.np), g.smem, p, "phi_t_spec", k.cluster);
   launch_phi_t_reduce(c, p.partial, J, p.nslots, pr.slot_term.p, out);

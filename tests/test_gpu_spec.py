@@ -265,3 +265,32 @@ def test_multi_rhs_tensor_core_kernel(spec, oracle, N, K, C):
     obg = spec.outerbase(omg, x)
     assert relerr(obg.sqmm(t2, np.abs(A)), o["ob"].sqmm(t2, np.abs(A))) < 1e-9
     assert relerr(obg.matmul(t2, A[:, :3]), o["ob"].matmul(t2, A[:, :3])) < 1e-9  # fewer than 8 columns: vector kernels
+
+
+def test_host_pointer_calls_overlap_their_transfers(spec):
+    """outerbase::mm / tmm with HOST buffers (the reference's call signatures, bench.py's e2e): a page-locked result
+    buffer is written by the kernel itself, the input vector of Phi^T streams in on a second stream while the kernel
+    already consumes the rows that have arrived -- same bits as the staged copies on pageable buffers."""
+    import torch
+    N, K = 300_001, 300  # above OuterBase::kOverlapRows, ragged
+    om, x, y, terms, rng = make_problem(spec, N, K)
+    ob = spec.outerbase(om, x, dograd=False)
+    a, r = rng.normal(size=K), rng.normal(size=N)
+    y0, t0 = ob.matmul(terms, a), ob.tmatmul(terms, r)  # pageable numpy buffers
+    assert ob.spec_state(terms) == 1
+    yp = torch.empty(N, dtype=torch.float64).pin_memory()
+    rp = torch.empty(N, dtype=torch.float64).pin_memory()
+    gp = torch.empty(K, dtype=torch.float64).pin_memory()
+    rp.numpy()[:] = r
+    for rep in range(3):  # the arrival counter is reset per call
+        yp.zero_()
+        ob.matmul(terms, a, out=yp.numpy())
+        np.testing.assert_array_equal(yp.numpy(), y0)
+        ob.tmatmul(terms, rp.numpy(), out=gp.numpy())
+        np.testing.assert_array_equal(gp.numpy(), t0)
+    spec.set_option("spec", 0)  # interpreter kernels: no streamed input, same call
+    try:
+        assert relerr(ob.tmatmul(terms, rp.numpy()), t0) < 1e-12
+        np.testing.assert_allclose(ob.matmul(terms, a, out=yp.numpy()), y0, rtol=0, atol=1e-12 * np.abs(y0).max())
+    finally:
+        spec.set_option("spec", 1)

@@ -9,11 +9,11 @@ import pytest
 REPO = Path(__file__).resolve().parents[1]
 
 
-def _run(backend, nproc, port):
+def _run(backend, nproc, port, extra_env=None):
     # the oracle's OpenMP regions ask for omp_get_num_procs() threads each (modandbase.cpp:464): cap them, or nproc ranks
     # oversubscribe the host nproc-fold and spin in each other's barriers
     per_rank = str(max(2, (os.cpu_count() or 2) // nproc))
-    env = dict(os.environ, OMP_NUM_THREADS="2", OMP_THREAD_LIMIT=per_rank, OMP_WAIT_POLICY="passive")
+    env = dict(os.environ, OMP_NUM_THREADS="2", OMP_THREAD_LIMIT=per_rank, OMP_WAIT_POLICY="passive", **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(REPO / "tests" / "mgpu_worker.py"), backend]
     return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
@@ -34,4 +34,8 @@ def test_row_sharding_nccl(gpu):
     if n < 2:
         pytest.skip("single-GPU box")
     res = _run("nccl", n, 29542)  # every visible GPU (8 on the scaling box)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    # the same on the terms-specialised kernels: Phi^T reduces over CTAs AND ranks in its own tail, optcg keeps its
+    # vectors in HBM (the sum of squared residuals rides on the fused allreduce)
+    res = _run("nccl", n, 29543, {"OB_SPEC": "1"})
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
