@@ -335,6 +335,18 @@ def run_special(args, lib, om, terms, x, cfg, rank, world, local, N, W, Lcols):
     barrier()
     ms = (time.perf_counter() - t0) / args.steps * 1e3
     launches = lib.launch_count() - n0
+    # what a BFGS objective evaluation pays (R/outersupport.R:215-216 -> loglik_gauss::updateom): the same rebuild on the
+    # columns the terms table reads (compact layout)
+    yv = wingweight(x); yv = (yv - yv.mean()) / yv.std(ddof=1)
+    loglik = lib.loglik_gauss(om, terms, yv, x)
+    for _ in range(3):
+        loglik.updateom()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loglik.updateom()
+    barrier()
+    ms_pruned = (time.perf_counter() - t0) / args.steps * 1e3
     clk = clocks.stop() if clocks else None
     if rank != 0:
         return
@@ -354,6 +366,8 @@ def run_special(args, lib, om, terms, x, cfg, rank, world, local, N, W, Lcols):
             "roofline": {"bound": "tensor", "kernel": "basis_build_mma_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": None, "peak_source": "FP64 pipe (DFMA micro-benchmark of this process; DMMA shares it)", "algorithmic_flop_per_launch": flop / d,
                          "hbm": {"achieved_gbs": bytes_w / (ms * 1e-3) / 1e9, "peak_gbs": hp, "peak_source": hs, "algorithmic_bytes_per_build": bytes_w}},
+            "pruned": {"ms": ms_pruned, "columns": int(np.asarray(terms).max(0).sum() + 3 * d), "of": int(M),
+                       "note": "loglik_gauss::updateom: levels the terms table reads (+2), the layout every objective evaluation rebuilds"},
             "clocks": clk}
     print(json.dumps(line))
 

@@ -176,6 +176,7 @@ int ob_outerbase_get_real(ob_outerbase* ob, const char* which, double* out, uint
   const std::string w = which;
   obe::OuterBase& b = *ob->ob;
   const double* src = nullptr;
+  if (w == "basemat" || w == "basemat_gradhyp") b.ensure_all(); /* the reference's full layout (modandbase.cpp:521-539) */
   if (w == "basemat") { src = b.basemat.p; *nrow = b.N; *ncol = b.M; }
   else if (w == "basemat_gradhyp") { if (!b.dograd) throw std::invalid_argument("built without gradients"); src = b.basematge.p; *nrow = b.N; *ncol = b.Mge; }
   else if (w == "basescale") { src = b.scale.p; *nrow = b.N; *ncol = 1; }

@@ -290,6 +290,7 @@ void launch_cg_stage(Ctx& c, const CgParams& p);
 /* basis build: cov(x, knots) . rotmat, normalise (modandbase.cpp:285-327, 547-626) */
 struct BuildDims {
   int kind; int m; int nh;
+  int mo = 0;    /* leading columns (levels 0 .. mo-1) to build and store; 0 = all m */
   double hyp[2];
   u64 knot_off;  /* offset of this dim's knots in the transformed-knot arrays */
   u64 col_off;   /* knotptst[l] */

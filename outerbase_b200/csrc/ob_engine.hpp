@@ -45,6 +45,16 @@ struct OuterBase {
   u64 nthreads = 1;
   u64 om_version = 0;
   std::vector<u64> knotptst, gest, hypmatch, hypst;
+  /* COMPACT column layout.  The reference builds and stores all m_l columns of every dimension (basemat N x M,
+   * basemat_gradhyp N x sum H_l m_l: modandbase.cpp:521-539, 547-626), but the products read only levels up to the
+   * highest one in `terms` -- 75 of 400 columns at C3.  Here dimension l holds mo[l] <= m_l columns
+   * (levels 0 .. mo[l]-1) starting at column cst[l]; hyper-parameter h of dimension l holds mo[l] gradient columns
+   * starting at cge[h].  mo grows on demand (need_levels: a terms table that reaches higher is built for before it is
+   * multiplied) and is complete (mo = m, cst = knotptst, cge = gest) whenever somebody asks for the matrices
+   * themselves (getbase, get_real: ensure_all).  Objects created from R-level `new(outerbase, om, x)` start complete;
+   * the lpdf classes know their terms and start pruned. */
+  std::vector<u64> mo, cst, cge;
+  u64 Mc = 0, Mgec = 0;
   DevBuf<double> x, basemat, basematge, scalemat, scale;
   /* basematsq (modandbase.cpp:527-531), materialised at the first squared operator after a build: squaring the staged
    * tile inside the Phi kernels instead made every squared product 3x slower than the plain one, and a BFGS
@@ -53,8 +63,8 @@ struct OuterBase {
   bool sq_valid = false;
   const double* sq_matrix() {
     if (!sq_valid) {
-      basematsq.ensure(ld * M);
-      obd::launch_square(ctx, basemat.p, ld * M, basematsq.p);
+      basematsq.ensure(ld * Mc);
+      obd::launch_square(ctx, basemat.p, ld * Mc, basematsq.p);
       sq_valid = true;
     }
     return basematsq.p;
@@ -92,9 +102,20 @@ struct OuterBase {
   std::vector<u64> cur_terms;
   u64 cur_K = 0;
 
-  OuterBase(Ctx& c, const OuterMod* om_, const double* xh, u64 N_, bool dograd_) : ctx(c), om(om_), N(N_), dograd(dograd_) {
+  /* hint_terms (K x d): the table the owner is going to multiply with -- the basis is built for its levels only */
+  OuterBase(Ctx& c, const OuterMod* om_, const double* xh, u64 N_, bool dograd_, const u64* hint_terms = nullptr, u64 hint_K = 0)
+      : ctx(c), om(om_), N(N_), dograd(dograd_) {
     if (!om->knots_set) throw std::range_error("Need to set covfs and knots before building.");
     d = om->d;
+    static const bool prune = !(getenv("OB_PRUNE") && std::string(getenv("OB_PRUNE")) == "0");
+    if (hint_terms && hint_K && prune) {
+      mo.assign(d, 1);
+      for (u64 l = 0; l < d; ++l) {
+        u64 mx = 0;
+        for (u64 k = 0; k < hint_K; ++k) mx = std::max(mx, hint_terms[k + l * hint_K]);
+        mo[l] = mx + 1 + kLevelMargin;
+      }
+    }
     ld = pad128(N);
     nthreads = 1;
     /* x is copied (modandbase.h:60), column by column into the padded layout */
@@ -116,6 +137,9 @@ struct OuterBase {
     knotptst.assign(kp, kp + d + 1);
     if (knotptst[d] > M) throw std::range_error("knotptst exceeds the columns of basemat");
     if (bmge) { gest.assign(ge, ge + H + 1); hypmatch.assign(hm, hm + H); }
+    mo.resize(d);
+    for (u64 l = 0; l < d; ++l) mo[l] = knotptst[l + 1] - knotptst[l];
+    cst = knotptst; cge = gest; Mc = M; Mgec = Mge; /* the caller's matrices: complete layout */
     auto put = [&](DevBuf<double>& dst, const double* src, u64 ncol) {
       dst.ensure(ld * std::max<u64>(ncol, 1));
       OB_CUDA(cudaMemsetAsync(dst.p, 0, ld * std::max<u64>(ncol, 1) * sizeof(double), ctx.stream));
@@ -136,18 +160,45 @@ struct OuterBase {
     }
   }
 
+  static constexpr u64 kLevelMargin = 2; /* levels built beyond the highest one seen: selectterms grows tables level by level */
+  /* a new terms table: rebuild first when it reaches levels the compact layout does not hold */
+  void need_levels(const u64* terms, u64 K) {
+    if (!om) return;
+    bool grow = false;
+    for (u64 l = 0; l < d; ++l) {
+      u64 mx = 0;
+      for (u64 k = 0; k < K; ++k) mx = std::max(mx, terms[k + l * K]);
+      if (mx + 1 > mo[l]) { mo[l] = mx + 1 + kLevelMargin; grow = true; }
+    }
+    if (grow) build();
+  }
+  bool complete() const {
+    for (u64 l = 0; l < d; ++l) if (mo[l] < knotptst[l + 1] - knotptst[l]) return false;
+    return true;
+  }
+  void ensure_all() { /* the matrices themselves are asked for: the reference's full layout */
+    if (!om || complete()) return;
+    for (u64 l = 0; l < d; ++l) mo[l] = knotptst[l + 1] - knotptst[l];
+    build();
+  }
   /* outerbase::build (modandbase.cpp:547-626): re-reads the CURRENT state of om */
   void build() {
     if (!om) throw std::logic_error("this outerbase wraps caller-provided matrices");
     if (knotptst != om->knotptst || d != om->d) { /* cached programs were bounds-checked against the OLD knot counts */
       coltables.clear(); programs.clear(); specs.clear();
+      if (!knotptst.empty()) mo.clear(); /* the knot layout changed under us (setknot): start complete again */
     }
     d = om->d; hypmatch = om->hypmatch; hypst = om->hypst; gest = om->gest; knotptst = om->knotptst; /* setvals_ :492 */
     H = hypmatch.size();
     M = om->nknot();
     Mge = om->nge();
-    basemat.ensure(ld * M);
-    if (dograd) basematge.ensure(ld * Mge);
+    if (mo.size() != d) { mo.resize(d); for (u64 l = 0; l < d; ++l) mo[l] = knotptst[l + 1] - knotptst[l]; }
+    cst.assign(d + 1, 0); cge.assign(H + 1, 0);
+    for (u64 l = 0; l < d; ++l) { mo[l] = std::max<u64>(1, std::min(mo[l], knotptst[l + 1] - knotptst[l])); cst[l + 1] = cst[l] + mo[l]; }
+    for (u64 h = 0; h < H; ++h) cge[h + 1] = cge[h] + mo[hypmatch[h]];
+    Mc = cst[d]; Mgec = cge[H];
+    basemat.ensure(ld * Mc);
+    if (dograd) basematge.ensure(ld * Mgec);
     scalemat.ensure(ld * d);
     scale.ensure(ld);
     knots_dev.upload(om->knotpt, ctx.stream);
@@ -158,8 +209,8 @@ struct OuterBase {
       obd::BuildDims& D = dims[l];
       D.kind = om->cov[l].kind; D.m = (int)om->mdim(l); D.nh = om->cov[l].numhyp;
       D.hyp[0] = om->hyp[hypst[l]]; D.hyp[1] = D.nh > 1 ? om->hyp[hypst[l] + 1] : 0.0;
-      D.knot_off = knotptst[l]; D.col_off = knotptst[l]; D.rot_off = knotptst[l];
-      for (int h = 0; h < D.nh; ++h) { D.ge_off[h] = gest[hypst[l] + h]; D.rotg_off[h] = gest[hypst[l] + h]; }
+      D.knot_off = knotptst[l]; D.col_off = cst[l]; D.rot_off = knotptst[l]; D.mo = (int)mo[l];
+      for (int h = 0; h < D.nh; ++h) { D.ge_off[h] = cge[hypst[l] + h]; D.rotg_off[h] = gest[hypst[l] + h]; }
     }
     obd::launch_basis_build(ctx, dims, x.p, N, ld, knots_dev.p, rot_dev.p, om->rotmat.nr, rotg_dev.p, basemat.p,
                             dograd ? basematge.p : nullptr, scalemat.p, scale.p, dograd);
@@ -186,6 +237,7 @@ struct OuterBase {
         return programs.front().prog.get();
       }
     check_terms(terms, K);
+    need_levels(terms, K);
     ProgEntry e;
     e.terms.assign(terms, terms + K * d);
     e.K = K; e.aug = aug; e.G = G; e.cap = cap;
@@ -216,6 +268,7 @@ struct OuterBase {
       }
     if (!e) {
       check_terms(terms, K);
+      need_levels(terms, K);
       specs.emplace_front();
       e = &specs.front();
       e->terms.assign(terms, terms + K * d);
@@ -308,7 +361,7 @@ struct OuterBase {
     if (!e) return false;
     obd::DotArgs g;
     g.gmat = basematge.p; g.bmat = sq ? basemat.p : nullptr; g.ld = ld; g.H = (int)H; g.d = (int)d;
-    g.hypst = hypst.data(); g.gest = gest.data(); g.knotptst = knotptst.data();
+    g.hypst = hypst.data(); g.gest = cge.data(); g.knotptst = cst.data();
     return obd::launch_phi_d_spec(ctx, *e->k, plan(e->pa.get(), sq, -1), a_dev, w_dev, g, out_dev);
   }
   bool gradhyp_dots_spec(const u64* terms, u64 K, const std::vector<double>& coeff_host, const double* w_dev, const double* yhat_dev,
@@ -341,7 +394,7 @@ struct OuterBase {
     for (u64 l = 0; l < d; ++l) {
       for (size_t c = 0; c < nc; ++c) {
         const obt::ColRef& cr = P.cols[c];
-        e->gsrc_host[l * nc + c] = cr.dim == l ? tmpC.p + (cr.level - 1) * ld : basemat.p + (knotptst[cr.dim] + cr.level) * ld;
+        e->gsrc_host[l * nc + c] = cr.dim == l ? tmpC.p + (cr.level - 1) * ld : basemat.p + (cst[cr.dim] + cr.level) * ld;
       }
       obd::ColTable& ct = *e->gtab[l];
       ct.ncol = ct.nload = (int)nc; ct.has_ops = false;
@@ -351,8 +404,8 @@ struct OuterBase {
     tmpHp.ensure(H * (u64)ctx.sms);
     for (u64 h = 0; h < H; ++h) {
       const u64 l = hypmatch[h];
-      const double* G = basematge.p + gest[h] * ld;
-      obd::launch_gradcols(ctx, basemat.p + knotptst[l] * ld, G, ld, lmax[l], tmpC.p);
+      const double* G = basematge.p + cge[h] * ld;
+      obd::launch_gradcols(ctx, basemat.p + cst[l] * ld, G, ld, lmax[l], tmpC.p);
       obd::PhiPlan pl;
       pl.prog = e->pa.get(); pl.cols = e->gtab[l].get(); pl.scale = scale.p; pl.sq = 0; pl.N = N;
       obd::PhiAArgs a;
@@ -373,14 +426,14 @@ struct OuterBase {
     std::vector<const double*> aux;
     for (const obt::ColRef& cr : P.cols) {
       if (!cr.aug) {
-        src.push_back((sq ? sq_matrix() : basemat.p) + (knotptst[cr.dim] + cr.level) * ld);
+        src.push_back((sq ? sq_matrix() : basemat.p) + (cst[cr.dim] + cr.level) * ld);
         ops.push_back(obd::COL_COPY);
       } else {
         if (h < 0 || hypmatch[h] != cr.dim || !dograd) throw std::logic_error("gradient column without a hyper-parameter");
-        src.push_back(basematge.p + (gest[h] + cr.level) * ld);
+        src.push_back(basematge.p + (cge[h] + cr.level) * ld);
         if (sq) { /* basematsq_gradhyp = 2*(Rt % R), modandbase.cpp:588-590 */
           ops.push_back(obd::COL_TWO_G_B | (int)((P.cols.size() + aux.size()) << 8));
-          aux.push_back(basemat.p + (knotptst[cr.dim] + cr.level) * ld);
+          aux.push_back(basemat.p + (cst[cr.dim] + cr.level) * ld);
         } else ops.push_back(obd::COL_COPY);
       }
     }
@@ -454,7 +507,7 @@ struct OuterBase {
       for (size_t c = 0; c < nc; ++c) {
         const obt::ColRef& cr = P.cols[c];
         const bool mine = cr.dim == l;
-        e->gsrc_t_host[l * nc + c] = mine ? tmpC.p + (cr.level - 1) * ld : (sq ? sq_matrix() : basemat.p) + (knotptst[cr.dim] + cr.level) * ld;
+        e->gsrc_t_host[l * nc + c] = mine ? tmpC.p + (cr.level - 1) * ld : (sq ? sq_matrix() : basemat.p) + (cst[cr.dim] + cr.level) * ld;
         e->gops_t_host[l * nc + c] = obd::COL_COPY;
       }
       obd::ColTable& ct = *e->gtab_t[l];
@@ -464,10 +517,10 @@ struct OuterBase {
     }
     for (u64 h = 0; h < H; ++h) {
       const u64 l = hypmatch[h];
-      const double* G = basematge.p + gest[h] * ld;
+      const double* G = basematge.p + cge[h] * ld;
       obd::launch_scaled_product(ctx, sq ? 2.0 : 1.0, G, w_dev, N, tmpNg.p); /* rows beyond N are masked by the kernel */
       obd::launch_phi_t_spec(ctx, *e->k, plan(e->pt.get(), sq, -1), tmpNg.p, tmpK2.p, ws);
-      obd::launch_gradcols(ctx, basemat.p + knotptst[l] * ld, G, ld, lmax[l], tmpC.p, sq);
+      obd::launch_gradcols(ctx, basemat.p + cst[l] * ld, G, ld, lmax[l], tmpC.p, sq);
       obd::PhiPlan pl;
       pl.prog = e->pt.get(); pl.cols = e->gtab_t[l].get(); pl.scale = scale.p; pl.sq = sq; pl.N = N;
       obd::launch_phi_t_spec(ctx, *e->k, pl, w_dev, tmpK2.p + K, ws);
@@ -594,9 +647,10 @@ struct OuterBase {
   }
   void getbase(u64 dim1, double* out) {
     if (dim1 < 1 || dim1 > d) throw std::range_error("dim out of range");
+    ensure_all();
     const u64 l = dim1 - 1, m = knotptst[l + 1] - knotptst[l];
     tmpP.ensure(N * m + 1);
-    obd::launch_getbase(ctx, basemat.p, scalemat.p + l * ld, N, ld, knotptst[l], m, tmpP.p);
+    obd::launch_getbase(ctx, basemat.p, scalemat.p + l * ld, N, ld, cst[l], m, tmpP.p);
     d2h(out, tmpP.p, N * m);
   }
 };
@@ -783,7 +837,7 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
   bool yhat_valid = false;
 
   LoglikGauss(Ctx& c, const OuterMod* om_, const u64* t, u64 K, const double* yh, const double* xh, u64 N_)
-      : ctx(c), om(om_), ob(c, om_, xh, N_, true), N(N_) {
+      : ctx(c), om(om_), ob(c, om_, xh, N_, true, t, K), N(N_) {
     d = om->d; npara = 1;
     terms.assign(t, t + K * d);
     nterms = K;
@@ -1000,7 +1054,7 @@ struct LoglikGda : Lpdf {
   std::vector<double> yhat, obssd, yhatge, obssd_gradhyp, obssd_gradpara, residtemp, residtemp2;
 
   LoglikGda(Ctx& c, const OuterMod* om_, const u64* t, u64 K, const double* yh, const double* xh, u64 N_)
-      : ctx(c), om(om_), ob(c, om_, xh, N_, true), N(N_) {
+      : ctx(c), om(om_), ob(c, om_, xh, N_, true, t, K), N(N_) {
     if (ctx.nranks > 1) throw std::logic_error("loglik_gda is the single-rank subsample model of obfit stage 1");
     d = om->d; npara = 2;
     terms.assign(t, t + K * d);
@@ -1336,7 +1390,7 @@ struct PredGauss { /* loglik_gauss.cpp:196-227 */
   int nthreads = 0;
   std::unique_ptr<OuterBase> ob;
   PredGauss(LoglikGauss& lk) : ctx(lk.ctx), om(lk.om), para(lk.para), coeff(lk.coeff), terms(lk.terms), K(lk.nterms), d(lk.d) {
-    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false));
+    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false, terms.data(), K));
     nthreads = (int)lk.ob.nthreads;
     if (coeff.size() != K) coeff.assign(K, 0.0);
     if (!lk.didnotothess) {
@@ -1344,7 +1398,7 @@ struct PredGauss { /* loglik_gauss.cpp:196-227 */
       for (u64 i = 0; i < coeffvar.size(); ++i) coeffvar[i] = 1 / lk.totdiaghess[i];
     } else coeffvar.assign(coeff.size(), 0.0);
   }
-  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false)); }
+  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false, terms.data(), K)); }
   void mean(double* out) { ob->mm(0, terms.data(), K, coeff.data(), out); }
   void var(double* out) {
     ob->mm(1, terms.data(), K, coeffvar.data(), out);
@@ -1362,14 +1416,14 @@ struct PredGda { /* loglik_gda.cpp:249-283 */
   bool doda;
   std::unique_ptr<OuterBase> ob;
   PredGda(LoglikGda& lk) : ctx(lk.ctx), om(lk.om), para(lk.para), coeff(lk.coeff), terms(lk.terms), K(lk.nterms), d(lk.d), doda(lk.doda) {
-    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false));
+    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false, terms.data(), K));
     if (coeff.size() != K) coeff.assign(K, 0.0);
     if (!lk.didnotothess) {
       coeffvar.resize(lk.totdiaghess.size());
       for (u64 i = 0; i < coeffvar.size(); ++i) coeffvar[i] = 1 / lk.totdiaghess[i];
     } else coeffvar.assign(coeff.size(), 0.0);
   }
-  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false)); }
+  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false, terms.data(), K)); }
   void mean(double* out) { ob->mm(0, terms.data(), K, coeff.data(), out); }
   void var(double* out) {
     ob->mm(1, terms.data(), K, coeffvar.data(), out);

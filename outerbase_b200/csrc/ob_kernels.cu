@@ -591,6 +591,7 @@ __global__ void cov_kernel(int kind, double h0, double h1, const double* x1, uns
 
 struct BuildKParams {
   int kind, m, nh, mp; /* mp: padded row length of the transposed rotation blocks in smem */
+  int mo;              /* columns built and stored (levels 0 .. mo-1 of the m): the contraction still runs over all m knots */
   double h0, h1;
   const double* knots;  /* this dim's m knots */
   const double* x;      /* this dim's column of x */
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(256) basis_build_kernel(const BuildKParams p) 
   double p0 = 0.0;
   for (int pp = 0; pp < m; ++pp) p0 = fma(Cs[(size_t)pp * ROWS + r], rotT[(size_t)pp * mp], p0);
   if (cg == 0 && row < p.ld) p.scalecol[row] = live ? p0 : 0.0;
-  for (int j0 = cg * 4; j0 < m; j0 += NCG * 4) {
+  for (int j0 = cg * 4; j0 < p.mo; j0 += NCG * 4) {
     double acc[4] = {0, 0, 0, 0}, s1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, s2[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     for (int pp = 0; pp < m; ++pp) {
       const double c = Cs[(size_t)pp * ROWS + r];
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(256) basis_build_kernel(const BuildKParams p) 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int j = j0 + q;
-        if (j >= m) break;
+        if (j >= p.mo) break;
         double v = 0.0;
         if (live) v = (j == 0) ? 1.0 : acc[q] / p0;
         p.bm[row + (unsigned long long)j * p.ld] = v;
@@ -713,14 +714,15 @@ __global__ void __launch_bounds__(256) basis_build_mma_kernel(const BuildKParams
   double* xt = kt + 2 * m;                              /* 2*ROWS row transforms */
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, k4 = lane & 3;
-  const int ntiles = (m + 7) / 8;
+  const int mo = p.mo < NT * 8 ? p.mo : NT * 8;
+  const int ntiles = (mo + 7) / 8;
 
   /* once per CTA: rotation blocks, knot transforms, zero padding (persistent CTAs walk the row tiles) */
   for (int idx = tid; idx < (1 + nh) * mk * RS; idx += 256) rotT[idx] = 0.0;
   for (int idx = tid; idx < (1 + nh) * mk * CS; idx += 256) Cs[idx] = 0.0;
   __syncthreads();
-  for (int idx = tid; idx < m * m; idx += 256) {
-    const int pp = idx % m, j = idx / m; /* column-major source: element (pp, j) */
+  for (int idx = tid; idx < m * mo; idx += 256) {
+    const int pp = idx % m, j = idx / m; /* column-major source: element (pp, j), the first mo columns */
     rotT[(size_t)pp * RS + j] = p.rot[pp + (unsigned long long)j * p.rot_ld];
     if (nh > 0) rotT[(size_t)(mk + pp) * RS + j] = p.rotg0[pp + (unsigned long long)j * p.rot_ld];
     if (nh > 1) rotT[(size_t)(2 * mk + pp) * RS + j] = p.rotg1[pp + (unsigned long long)j * p.rot_ld];
@@ -792,7 +794,7 @@ __global__ void __launch_bounds__(256) basis_build_mma_kernel(const BuildKParams
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = jt * 8 + 2 * k4 + e;
-          if (j < m) {
+          if (j < mo) {
             double v = 0.0;
             if (live) v = (j == 0) ? 1.0 : acc[0][jt][e] / p0;
             p.bm[row + (unsigned long long)j * p.ld] = v;
@@ -1578,6 +1580,7 @@ void launch_basis_build(Ctx& c, const std::vector<BuildDims>& dims, const double
     p.bg1 = dograd && D.nh > 1 ? basematge + D.ge_off[1] * ld : nullptr;
     p.scalecol = scalemat + l * ld;
     p.N = N; p.ld = ld; p.dograd = dograd ? 1 : 0;
+    p.mo = D.mo > 0 && D.mo < D.m ? D.mo : D.m;
     const int nh = dograd ? D.nh : 0;
     auto need = [&](int rows) {
       return ((size_t)(1 + nh) * D.m * p.mp + (size_t)(1 + nh) * D.m * rows + 2 * D.m + 2 * rows) * sizeof(double);
@@ -1587,13 +1590,21 @@ void launch_basis_build(Ctx& c, const std::vector<BuildDims>& dims, const double
       return ((size_t)(1 + nh) * mk * (nt * 8 + 4) + (size_t)(1 + nh) * mk * 72 + 2 * D.m + 2 * 64) * sizeof(double);
     };
     static const bool use_mma = !(getenv("OB_BUILD") && std::string(getenv("OB_BUILD")) == "fma");
-    if (use_mma && D.m <= 40 && need_mma(5) <= c.smem_optin) {
-      set_smem(basis_build_mma_kernel<5>, need_mma(5));
-      basis_build_mma_kernel<5><<<(unsigned)std::min<u64>((ld + 63) / 64, (u64)c.sms * 2), 256, need_mma(5), c.stream>>>(p);
-    } else if (use_mma && D.m <= 72 && need_mma(9) <= c.smem_optin) {
-      set_smem(basis_build_mma_kernel<9>, need_mma(9));
-      basis_build_mma_kernel<9><<<(unsigned)std::min<u64>((ld + 63) / 64, (u64)c.sms), 256, need_mma(9), c.stream>>>(p);
-    } else if (need(64) <= c.smem_optin) {
+    /* column tiles of 8: the smallest instantiation that covers the columns to build (the accumulators of a tile
+     * live in registers, so the count is a template argument); 2 CTAs per SM up to 5 tiles */
+#define OB_BUILD_MMA(NT_, PER_SM)                                                                                   \
+    {                                                                                                               \
+      set_smem(basis_build_mma_kernel<NT_>, need_mma(NT_));                                                         \
+      basis_build_mma_kernel<NT_><<<(unsigned)std::min<u64>((ld + 63) / 64, (u64)c.sms * PER_SM), 256, need_mma(NT_), c.stream>>>(p); \
+    }
+    const int nt = (p.mo + 7) / 8;
+    if (use_mma && D.m <= 72 && nt <= 1 && need_mma(1) <= c.smem_optin) OB_BUILD_MMA(1, 2)
+    else if (use_mma && D.m <= 72 && nt <= 2 && need_mma(2) <= c.smem_optin) OB_BUILD_MMA(2, 2)
+    else if (use_mma && D.m <= 72 && nt <= 3 && need_mma(3) <= c.smem_optin) OB_BUILD_MMA(3, 2)
+    else if (use_mma && D.m <= 72 && nt <= 5 && need_mma(5) <= c.smem_optin) OB_BUILD_MMA(5, 2)
+    else if (use_mma && D.m <= 72 && need_mma(9) <= c.smem_optin) OB_BUILD_MMA(9, 1)
+#undef OB_BUILD_MMA
+    else if (need(64) <= c.smem_optin) {
       set_smem(basis_build_kernel<64>, need(64));
       basis_build_kernel<64><<<(unsigned)((ld + 63) / 64), 256, need(64), c.stream>>>(p);
     } else if (need(32) <= c.smem_optin) {

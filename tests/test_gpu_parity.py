@@ -353,3 +353,32 @@ def test_loglik_gda_parity(gpu, oracle, N, K):
     assert relerr(g["vcoeff"], o["vcoeff"]) < 1e-8
     assert relerr(g["vgh"], o["vgh"]) < 1e-6 and relerr(g["vgp"], o["vgp"]) < 1e-7
     assert relerr(g["mean"], o["mean"]) < 1e-7 and relerr(g["var"], o["var"]) < 1e-7
+
+
+def test_pruned_basis_layout_grows_with_the_terms(gpu, oracle):
+    """The lpdf classes build only the basis columns their terms table reads (compact layout, ob_engine.hpp): a table that
+    reaches higher levels -- updateterms, as obfit's rounds do (R/fitting.R:118-120) -- is built for before it is
+    multiplied; hyper-parameter updates rebuild the compact layout; the matrices themselves stay available in full."""
+    N = 3000
+    res = {}
+    for name, lib in (("g", gpu), ("o", oracle)):
+        om, x, y, t_small, rng = make_problem(lib, N, 30)
+        t_big = om.selectterms(600)
+        assert t_big.max() > t_small.max() + 2
+        lk = lib.loglik_gauss(om, t_small, y, x)
+        lk.compute_gradhyp = True; lk.compute_gradpara = True
+        c_small, c_big = rng.normal(size=30) / 50, rng.normal(size=600) / 200
+        lk.update(c_small)
+        first = (lk.val, np.array(lk.grad), np.array(lk.gradhyp))
+        lk.updateterms(t_big)
+        lk.update(c_big)
+        second = (lk.val, np.array(lk.grad), np.array(lk.gradhyp), lk.diaghess(), lk.diaghessgradhyp())
+        hyp = om.gethyp() + 0.03
+        om.updatehyp(hyp); lk.updateom()
+        lk.update(c_big)
+        third = (lk.val, np.array(lk.grad), np.array(lk.gradhyp))
+        res[name] = (first, second, third)
+    for a, b in zip(res["g"], res["o"]):
+        assert abs(a[0] - b[0]) <= 1e-8 * abs(b[0])
+        assert relerr(a[1], b[1]) < 1e-8 and relerr(a[2], b[2]) < 1e-7
+    assert relerr(res["g"][1][3], res["o"][1][3]) < 1e-8 and relerr(res["g"][1][4], res["o"][1][4]) < 1e-7
