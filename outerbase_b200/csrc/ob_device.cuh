@@ -218,11 +218,6 @@ struct Workspace {
 };
 
 int phi_grid(const Ctx& c, u64 N, int tile_rows);
-/* second-generation (TMEM) kernels: enabled unless OB_PHI=v1; need a 4-group program with shallow stacks */
-bool tmem_kernels_enabled(int dir);
-bool tmem_eligible(const obt::Program& P);
-bool tmem_fits(const Ctx& c, const DevProgram& pr, int ncol, u64 N);
-int tmem_rows_per_lane(const Ctx& c, u64 N); /* R of the TMEM kernels for N rows: 4 (256-row team tiles) or 2 */
 /* Phi a (trie/Horner kernel, or the brute-force kernel when the program is not fast_ok) */
 void launch_phi_a(Ctx& c, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);
 /* Phi^T w -> out (K, device); result is the LOCAL (this rank's rows) sum */

@@ -220,14 +220,10 @@ struct OuterBase {
     om_version = om->version;
   }
 
-  /* the program an INTERPRETER Phi kernel runs (dir 0 = Phi a, 1 = Phi^T): the shared-memory kernels
-   * with 16 term groups; OB_PHI=v2 opts into the TMEM-resident interpreter (4 term groups).  Tables that
-   * prove hot run on the terms-specialised kernels instead (spec_for). */
+  /* the program an INTERPRETER Phi kernel runs (dir 0 = Phi a, 1 = Phi^T): 16 term groups, one per compute warp.
+   * Tables that prove hot run on the terms-specialised kernels instead (spec_for). */
   obd::DevProgram* program(const u64* terms, u64 K, int aug, int dir = 0) {
-    if (obd::tmem_kernels_enabled(dir)) {
-      obd::DevProgram* p4 = program_g(terms, K, aug, 4, 512 / (2 * obd::tmem_rows_per_lane(ctx, N)));
-      if (obd::tmem_eligible(p4->host) && obd::tmem_fits(ctx, *p4, (int)p4->host.cols.size(), N)) return p4;
-    }
+    (void)dir;
     return program_g(terms, K, aug, 16, 0);
   }
   obd::DevProgram* program_g(const u64* terms, u64 K, int aug, int G, int cap) {

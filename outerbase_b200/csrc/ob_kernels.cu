@@ -437,7 +437,6 @@ __global__ void __launch_bounds__(kPhiThreads, 1) phi_t_kernel(const PhiKParams 
   for (int i = tid; i < p.nslots; i += kPhiThreads) p.partial[(size_t)blockIdx.x * p.nslots + i] = acc_sm[i];
 }
 
-#include "ob_phi_tmem.cuh"
 
 /* out[term(slot)] = sum over CTAs, fixed order */
 __global__ void phi_t_reduce_kernel(const double* __restrict__ partial, int nblocks, int nslots,
@@ -1207,90 +1206,7 @@ static void set_smem(Kern k, size_t bytes) {
   OB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
-/* ---- second generation (TMEM) geometry */
-bool tmem_kernels_enabled(int dir) {
-  static int mode = -1; /* 0 default = v1 (shared-memory interpreter), 1 v1 only, 2 v2 (TMEM interpreter) for both */
-  if (mode < 0) {
-    const char* e = getenv("OB_PHI");
-    mode = !e ? 0 : (std::string(e) == "v1" ? 1 : (std::string(e) == "v2" ? 2 : 0));
-  }
-  (void)dir; /* large problems run on the terms-specialised kernels (ob_spec.hpp); v2 is opt-in (OB_PHI=v2) */
-  return mode == 2;
-}
-bool tmem_eligible(const obt::Program& P) { return P.fast_ok && P.G == 4 && P.fwd_stack <= 4 && P.bwd_stack <= 4; }
-
-int tmem_rows_per_lane(const Ctx& c, u64 N) { return N < (u64)c.sms * 2 * 256 ? 2 : 4; }
-
-struct Phi2Geom { int R = 0, lt = 0, ncs = 0, prog_in_smem = 0; size_t smem = 0; unsigned off_vec, off_prog, off_tile, tile_doubles, off_part; };
-/* R and the TMEM capacity are fixed when the program is compiled (its words carry the location
- * of every column); here only the shared-memory layout is decided */
-static Phi2Geom phi2_geometry(const Ctx& c, const DevProgram& pr, const ColTable& ct, bool is_a, u64 N) {
-  const size_t nwords = is_a ? pr.host.bwd.size() : pr.host.fwd.size();
-  const size_t vec_bytes = (((is_a ? 1 : 4) * pr.host.nslots() * sizeof(double) + 127) / 128) * 128;
-  const int cap = pr.host.tmem_cap;
-  if (cap != 64 && cap != 128) return Phi2Geom();
-  const int R = 512 / (2 * cap), TRT = 64 * R;
-  (void)N;
-  for (int pass = 0; pass < 2; ++pass) {
-    Phi2Geom g;
-    g.R = R;
-    g.lt = std::min(ct.ncol, cap);
-    g.ncs = ct.ncol - g.lt;
-    size_t off = 128;
-    g.off_vec = (unsigned)off; off += vec_bytes;
-    g.off_prog = (unsigned)off;
-    g.prog_in_smem = pass == 0;
-    if (g.prog_in_smem) off += ((nwords * 4 + 127) / 128) * 128;
-    g.off_tile = (unsigned)off;
-    g.tile_doubles = (unsigned)(g.ncs * TRT);
-    off += 2 * (size_t)g.tile_doubles * sizeof(double);
-    g.off_part = (unsigned)off;
-    if (is_a) off += (size_t)8 * TRT * sizeof(double);
-    else off += (size_t)16 * 16 * 33 * sizeof(double); /* per-warp emit staging */
-    g.smem = off;
-    if (g.smem <= c.smem_optin) return g;
-  }
-  return Phi2Geom();
-}
-static void fill_params2(PhiKParams& p, const PhiPlan& pl, const Phi2Geom& g, bool is_a) {
-  const DevProgram& pr = *pl.prog;
-  p.load_src = pl.cols->load_src.p; p.col_op = pl.cols->col_op.p;
-  p.ncol = pl.cols->ncol; p.nload = pl.cols->nload; p.has_ops = pl.cols->has_ops ? 1 : 0;
-  p.prog = is_a ? pr.bwd.p : pr.fwd.p;
-  p.prog_off = is_a ? pr.bwd_off.p : pr.fwd_off.p;
-  p.slot_base = pr.slot_base.p; p.slot_real = pr.slot_real.p; p.slot_term = pr.slot_term.p;
-  p.nslots = (int)pr.host.nslots();
-  p.nwords = (int)(is_a ? pr.host.bwd.size() : pr.host.fwd.size());
-  p.prog_in_smem = g.prog_in_smem;
-  p.scale = pl.scale; p.sq = pl.sq; p.N = pl.N;
-  p.ntiles = (int)((pl.N + 64 * g.R - 1) / (64 * g.R));
-  p.nbuf = 1;
-  p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles; p.off_vec = g.off_vec; p.off_prog = g.off_prog; p.off_part = g.off_part;
-  p.lt = g.lt; p.ncs = g.ncs;
-}
-bool tmem_fits(const Ctx& c, const DevProgram& pr, int ncol, u64 N) {
-  ColTable ct; ct.ncol = ncol; ct.nload = ncol;
-  return phi2_geometry(c, pr, ct, true, N).R != 0 && phi2_geometry(c, pr, ct, false, N).R != 0;
-}
-static int phi2_grid(const Ctx& c, const PhiKParams& p) { return std::max(1, std::min((p.ntiles + 1) / 2, c.sms)); }
-
 void launch_phi_a(Ctx& c, const PhiPlan& pl, const PhiAArgs& a, Workspace& ws, int* grid_out) {
-  if (pl.N > 0 && pl.prog->host.G == 4) {
-    const Phi2Geom g = phi2_geometry(c, *pl.prog, *pl.cols, true, pl.N);
-    if (g.R == 0) throw std::logic_error("TMEM kernel does not fit: caller must fall back to the G=16 program");
-    PhiKParams p{};
-    fill_params2(p, pl, g, true);
-    p.a = a.a; p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
-    const int grid = phi2_grid(c, p);
-    if (a.mode == PHI_UPDATE) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
-#define OB_L2(RR, PP) { set_smem(phi_a2_kernel<RR, PP>, g.smem); phi_a2_kernel<RR, PP><<<grid, 512, g.smem, c.stream>>>(p); }
-    if (g.R == 4) { if (g.prog_in_smem) OB_L2(4, true) else OB_L2(4, false) }
-    else { if (g.prog_in_smem) OB_L2(2, true) else OB_L2(2, false) }
-#undef OB_L2
-    check_launch(c, "phi_a2_kernel");
-    if (grid_out) *grid_out = grid;
-    return;
-  }
   const DevProgram& pr = *pl.prog;
   if (pl.N == 0) { if (grid_out) *grid_out = 0; return; }
   PhiGeom g;
@@ -1325,22 +1241,6 @@ void launch_phi_t(Ctx& c, const PhiPlan& pl, const double* w, double* out, Works
   const int K = (int)pr.host.K;
   if (K == 0) return;
   if (pl.N == 0) { launch_fill(c, out, K, 0.0); return; }
-  if (pr.host.G == 4) {
-    const Phi2Geom g = phi2_geometry(c, pr, *pl.cols, false, pl.N);
-    if (g.R == 0) throw std::logic_error("TMEM kernel does not fit: caller must fall back to the G=16 program");
-    PhiKParams p{};
-    fill_params2(p, pl, g, false);
-    const int grid = phi2_grid(c, p);
-    p.win = w;
-    p.partial = ws.partial.ensure((size_t)grid * p.nslots);
-#define OB_L2(RR, PP) { set_smem(phi_t2_kernel<RR, PP>, g.smem); phi_t2_kernel<RR, PP><<<grid, 512, g.smem, c.stream>>>(p); }
-    if (g.R == 4) { if (g.prog_in_smem) OB_L2(4, true) else OB_L2(4, false) }
-    else { if (g.prog_in_smem) OB_L2(2, true) else OB_L2(2, false) }
-#undef OB_L2
-    check_launch(c, "phi_t2_kernel");
-    launch_phi_t_reduce(c, p.partial, grid, p.nslots, pr.slot_term.p, out);
-    return;
-  }
   PhiGeom g;
   if (pr.host.fast_ok) g = phi_geometry(c, pr, *pl.cols, false, pl.N);
   if (g.R == 0) {
