@@ -82,7 +82,9 @@ struct DotParams {
 struct SpecOptions {
   /* Phi a (one stream = the whole program): rows per lane, passes per tile (= warps per tile), tiles
    * in work at once (compute warps = qa * tga), register-cached columns */
-  int ra = 1, qa = 4, tga = 2, cache_a = 80;
+  /* round 2: 64-row tiles, four in work (qa 2, tga 4) -- 0.272 against 0.282 ms at 1M rows and 44 against 47 us on a
+   * 125k-row shard (finer tail); all columns of C3 register-cached now that a compute warp has 232 registers */
+  int ra = 1, qa = 2, tga = 4, cache_a = 80;
   /* Phi^T: warps per CTA (= streams per CTA type), rows per lane, passes per tile, cached columns,
    * accumulators per warp (cap) */
   /* acc_cap bounds the LENGTH of a stream as much as its registers: the two compute warps of an SM sub-partition run
