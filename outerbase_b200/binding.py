@@ -100,6 +100,16 @@ class Library:
         self.call("spec_source", _p(t), _u(t.shape[0]), _u(t.shape[1]), o, buf, C.byref(n), info)
         return buf.value.decode(), dict(types=info[0], nacc=info[1], tile_rows_a=info[2], tile_rows_t=info[3])
 
+    def spec_source_tmat(self, terms):
+        """Source of the tensor-core Phi^T.A module (phi_tm_spec) for a table; info = {types, maxcols}."""
+        t = np.asfortranarray(terms, dtype=np.uint64)
+        n = C.c_uint64(0)
+        info = (C.c_uint64 * 2)()
+        self.call("spec_source_tmat", _p(t), _u(t.shape[0]), _u(t.shape[1]), None, C.byref(n), info)
+        buf = C.create_string_buffer(n.value)
+        self.call("spec_source_tmat", _p(t), _u(t.shape[0]), _u(t.shape[1]), buf, C.byref(n), info)
+        return buf.value.decode(), {"types": info[0], "maxcols": info[1]}
+
     def spec_source_dot(self, terms):
         """CUDA source of the hyper-gradient sweep kernel (phi_d_spec) for a terms table (host only) -> (source, info)."""
         t = _terms(terms)

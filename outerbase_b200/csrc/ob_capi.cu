@@ -308,6 +308,24 @@ int ob_spec_source_dot(const uint64_t* terms, uint64_t K, uint64_t d, char* buf,
   *len = S.src.size() + 1;
   OB_CATCH
 }
+int ob_spec_source_tmat(const uint64_t* terms, uint64_t K, uint64_t d, char* buf, uint64_t* len, uint64_t* info) {
+  OB_TRY
+  need(terms, "terms"); need(len, "len");
+  obs::SpecOptions o = obd::spec_default_options();
+  o.wt = obs::kTmWarps; o.acc_cap = obs::kTmTerms;
+  const int types = obs::choose_types(terms, K, d, o);
+  if (!types) throw std::invalid_argument("terms table is not trie-compilable (duplicate or too deep terms)");
+  const obt::Program pt = obt::compile(terms, K, d, types * obs::kTmWarps);
+  const obs::SpecSource S = obs::generate_tmat(pt, types, o);
+  if (!S.ok) throw std::invalid_argument(S.why);
+  if (info) { info[0] = (u64)S.types; info[1] = (u64)S.maxcols_t; }
+  if (buf) {
+    if (*len < S.src.size() + 1) throw std::range_error("buffer too small");
+    std::memcpy(buf, S.src.c_str(), S.src.size() + 1);
+  }
+  *len = S.src.size() + 1;
+  OB_CATCH
+}
 int ob_spec_compile_check(const char* source, uint64_t* cubin_bytes, double* seconds) {
   OB_TRY
   need(source, "source");

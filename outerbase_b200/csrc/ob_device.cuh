@@ -235,6 +235,7 @@ double spec_compile_seconds(const SpecKernels& k);
 std::string spec_compile_nocache(const std::string& src, double* seconds);
 bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol);
 bool spec_uses_cluster(const SpecKernels& k);
+bool launch_phi_tm_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, int types, const double* A, u64 lda, u64 C, double* out);
 /* true when [p, p + bytes) lies inside one device allocation (cuMemGetAddressRange through the runtime's driver entry point) */
 bool device_range_readable(const void* p, size_t bytes);
 void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs& args, Workspace& ws, int* grid_out);

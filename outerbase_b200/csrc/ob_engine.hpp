@@ -81,9 +81,9 @@ struct OuterBase {
    * Phi^T: types * wt streams) and the compiled module */
   struct SpecEntry {
     std::vector<u64> terms; u64 K = 0;
-    std::unique_ptr<obd::DevProgram> pa, pt;
+    std::unique_ptr<obd::DevProgram> pa, pt, ptm; /* ptm: streams of <= 32 terms for phi_tm_spec, built at first use */
     std::shared_ptr<obd::SpecKernels> k;
-    int types = 0;
+    int types = 0, types_m = 0;
     obs::SpecOptions opt;
     int state = 0;      /* 0 interpreter so far, 1 module ready, -1 not specialisable */
     bool probed = false; /* disk cache looked up */
@@ -271,7 +271,7 @@ struct OuterBase {
       e->K = K;
       while (specs.size() > 8) {
         const SpecEntry& dead = specs.back();
-        coltables.remove_if([&](const ColEntry& c) { return c.prog == dead.pa.get() || c.prog == dead.pt.get(); });
+        coltables.remove_if([&](const ColEntry& c) { return c.prog == dead.pa.get() || c.prog == dead.pt.get() || c.prog == dead.ptm.get(); });
         specs.pop_back();
       }
     }
@@ -598,7 +598,27 @@ struct OuterBase {
         if (obd::launch_phi_am_spec(ctx, *e->k, plan(e->pa.get(), sq, -1), A_dev, C, out_dev, ldo)) return;
     for (u64 c = 0; c < C; ++c) mm_dev(terms, K, sq, A_dev + c * K, out_dev + c * ldo);
   }
+  /* tprodmm_(mat), linalg.cpp:583-637: eight or more columns run as dense contractions over the rows on the FP64 tensor
+   * cores (phi_tm_spec) when the table is specialised; otherwise a column loop over the vector kernels */
   void tmm_mat_dev(const u64* terms, u64 K, int sq, const double* A_dev, u64 lda, u64 C, double* out_dev) {
+    if (C >= 8)
+      if (SpecEntry* e = spec_for(terms, K)) {
+        if (!e->ptm && e->types_m >= 0) {
+          obs::SpecOptions o = e->opt;
+          o.wt = obs::kTmWarps; o.acc_cap = obs::kTmTerms;
+          e->types_m = obs::choose_types(terms, K, d, o);
+          if (e->types_m > 0 && e->types_m <= ctx.sms) {
+            e->ptm.reset(new obd::DevProgram());
+            e->ptm->host = obt::compile(terms, K, d, e->types_m * obs::kTmWarps);
+            e->ptm->upload(ctx.stream);
+            ctx.sync();
+          } else e->types_m = -1;
+        }
+        if (e->ptm && obd::launch_phi_tm_spec(ctx, *e->k, plan(e->ptm.get(), sq, -1), e->types_m, A_dev, lda, C, out_dev)) {
+          ctx.allreduce_sum(out_dev, K * C);
+          return;
+        }
+      }
     for (u64 c = 0; c < C; ++c) tmm_dev(terms, K, sq, A_dev + c * lda, out_dev + c * K, false, std::min<u64>(ld, (C - c) * lda));
     ctx.allreduce_sum(out_dev, K * C);
   }

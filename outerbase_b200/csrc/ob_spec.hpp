@@ -65,6 +65,15 @@ struct MatParams {
   unsigned off_phi, off_coef;
 };
 
+/* mirrored by `struct TMatParams` in ob_spec_scaffold.inc (phi_tm_spec) */
+struct TMatParams {
+  const double* A;       /* N x ncols right-hand sides, column-major, leading dimension lda (padded like basemat) */
+  double* partial;       /* J x nslots x 64 per-row-group sums */
+  unsigned long long lda;
+  int ncols, nslots;
+  unsigned off_park, off_r; /* shared memory: per-warp Phi blocks | within a stage: offset of the 64 right-hand-side columns */
+};
+
 /* mirrored by `struct DotParams` in ob_spec_scaffold.inc (phi_d_spec) */
 struct DotParams {
   const double* gmat;    /* basemat_gradhyp: column gest[h] + j = G_h[:, j], leading dimension ld */
@@ -250,8 +259,10 @@ inline void emit_bwd(Emitter& e, const Program& P, int g, int R, int TR, int cac
 }
 
 /* forward (top-down) stream g -> statements accumulating into acc<i>; returns the emit count */
-inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cache, const std::vector<int>& pos) {
+inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cache, const std::vector<int>& pos, bool park = false) {
   using namespace obt;
+  /* park: every emit is Phi[row, term] itself and goes to the warp's shared-memory block (OBS_TM_PARK) instead of a
+   * register accumulator -- phi_tm_spec contracts the block with the right-hand sides on the tensor cores */
   Factors F(P, P.fwd, P.fwd_off[g], P.fwd_off[g + 1], true, cache, R, TR, &pos);
   int nv = 0, ia = 0;
   std::string cur = "b", stk[kMaxDepth + 2];
@@ -269,7 +280,8 @@ inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cach
     if (op == F_LEAF) {
       for (int r = 0; r < R; ++r) {
         const std::string f = F.get(e, (int)col, r);
-        e.f("acc%d = fma(%s, %s, acc%d);\n", ia, name(cur, r).c_str(), f.c_str(), ia);
+        if (park) e.f("OBS_TM_PARK(%d, %s * %s);\n", ia, name(cur, r).c_str(), f.c_str());
+        else e.f("acc%d = fma(%s, %s, acc%d);\n", ia, name(cur, r).c_str(), f.c_str(), ia);
       }
       ++ia;
     } else if (op == F_DESC_CUR || op == F_DESC_STK) {
@@ -282,11 +294,17 @@ inline int emit_fwd(Emitter& e, const Program& P, int g, int R, int TR, int cach
       cur = x;
       if (fl & FLAG_SAVE) stk[d] = x;
       if (fl & FLAG_EMIT) {
-        for (int r = 0; r < R; ++r) e.f("acc%d += %s_%d;\n", ia, x.c_str(), r);
+        for (int r = 0; r < R; ++r) {
+          if (park) e.f("OBS_TM_PARK(%d, %s_%d);\n", ia, x.c_str(), r);
+          else e.f("acc%d += %s_%d;\n", ia, x.c_str(), r);
+        }
         ++ia;
       }
     } else if (op == F_ROOT) {
-      for (int r = 0; r < R; ++r) e.f("acc%d += b[%d];\n", ia, r);
+      for (int r = 0; r < R; ++r) {
+        if (park) e.f("OBS_TM_PARK(%d, b[%d]);\n", ia, r);
+        else e.f("acc%d += b[%d];\n", ia, r);
+      }
       ++ia;
     } else if (op == F_LOADCUR) {
       cur = stk[d];
@@ -637,6 +655,63 @@ inline SpecSource generate_mat(const Program& pa, const SpecOptions& opt) {
   std::string src = scaffold_text();
   replace_marker(src, "//@@TABLES@@", tab.s);
   replace_marker(src, "//@@BODY_M@@", body.s);
+  S.src = hdr.s + src;
+  S.ok = true;
+  return S;
+}
+
+/* Phi^T . A on the tensor cores (phi_tm_spec only): pt = program compiled with G = types * 8 streams of at most
+ * kTmTerms terms each (choose_types with that cap) */
+constexpr int kTmTerms = 32, kTmWarps = 8;
+inline SpecSource generate_tmat(const Program& pt, int types, const SpecOptions& opt) {
+  using namespace detail;
+  SpecSource S;
+  S.opt = opt;
+  S.types = types;
+  S.tr_t = 64;
+  const int G = types * kTmWarps;
+  if (!pt.fast_ok || pt.G != G || pt.tmem_cap || pt.K == 0) { S.why = "program does not match"; return S; }
+  Emitter hdr, tab, ct;
+  hdr.f("#define OBS_PARAM_BYTES %d\n#define OBS_TM_BYTES %d\n#define OBS_K %llu\n#define OBS_NP 4\n#define OBS_HAVE_TM 1\n#define OBS_TYPES %d\n#define OBS_PSLEEP %d\n", (int)sizeof(SpecParams),
+        (int)sizeof(TMatParams), (unsigned long long)pt.K, types, opt.psleep);
+  hdr.f("#define OBS_NREG_C %d\n#define OBS_NREG_P %d\n", opt.nreg_c % 8 == 0 && opt.nreg_c >= 200 ? opt.nreg_c : 232, 40);
+  std::vector<std::vector<int>> tcols(types);
+  for (int g = 0; g < G; ++g) {
+    if ((int)pt.slot_real[g] > kTmTerms) { S.why = "stream longer than the Phi block"; return S; }
+    std::vector<char> used(pt.cols.size(), 0);
+    for (uint32_t i = pt.fwd_off[g]; i < pt.fwd_off[g + 1]; ++i) {
+      const uint32_t w = pt.fwd[i], op = w >> 28;
+      if (op >= 8 || op == obt::F_DESC_CUR || op == obt::F_DESC_STK) used[w & 0xFFFFu] = 1;
+    }
+    auto& tc = tcols[g / kTmWarps];
+    for (size_t c = 0; c < used.size(); ++c) if (used[c] && std::find(tc.begin(), tc.end(), (int)c) == tc.end()) tc.push_back((int)c);
+  }
+  size_t maxcols = 1;
+  for (auto& tc : tcols) { std::sort(tc.begin(), tc.end()); maxcols = std::max(maxcols, tc.size()); }
+  S.maxcols_t = (int)maxcols;
+  hdr.f("#define OBS_MAXCOLS_T %d\n", (int)maxcols);
+  tab.f("__device__ const unsigned short obs_cols_t[] = {");
+  std::vector<int> coff{0};
+  for (auto& tc : tcols) { for (int c : tc) tab.f("%d,", c); coff.push_back(coff.back() + (int)tc.size()); }
+  tab.f("0};\n__device__ const unsigned short obs_coff_t[] = {");
+  for (int v : coff) tab.f("%d,", v);
+  tab.f("};\n__device__ const unsigned obs_slot_base[] = {");
+  for (int g = 0; g < G; ++g) tab.f("%u,", pt.slot_base[g]);
+  tab.f("};\n__device__ const unsigned short obs_slot_real[] = {");
+  for (int g = 0; g < G; ++g) tab.f("%u,", pt.slot_real[g]);
+  tab.f("};\n");
+  for (int g = 0; g < G; ++g) {
+    const auto& tc = tcols[g / kTmWarps];
+    std::vector<int> pos(pt.cols.size(), -1);
+    for (size_t i = 0; i < tc.size(); ++i) pos[tc[i]] = (int)i;
+    ct.f("case %d: {\n", g);
+    const int n = emit_fwd(ct, pt, g, 1, S.tr_t, 0, pos, /*park=*/true);
+    if (n != (int)pt.slot_real[g]) { S.why = "emit count mismatch"; return S; }
+    ct.f("} break;\n");
+  }
+  std::string src = scaffold_text();
+  replace_marker(src, "//@@TABLES@@", tab.s);
+  replace_marker(src, "//@@CASES_TM@@", ct.s);
   S.src = hdr.s + src;
   S.ok = true;
   return S;

@@ -170,6 +170,12 @@ struct SpecKernels {
   int nblk = 0, mat_state = 0; /* 0 not built, 1 ready, -1 failed */
   size_t smem_m_set = 0;
   DevBuf<double> aperm;
+  /* transposed multi right-hand-side module (phi_tm_spec), built at first use */
+  cudaLibrary_t libtm = nullptr;
+  cudaKernel_t ktm = nullptr;
+  int tm_state = 0, tm_maxcols = 0; /* 0 not built, 1 ready, -1 failed */
+  size_t smem_tm_set = 0;
+  DevBuf<double> tm_partial, tm_stage;
   /* hyper-gradient sweep module (phi_d_spec), built at first use */
   cudaLibrary_t libd = nullptr;
   cudaKernel_t kd = nullptr;
@@ -180,7 +186,7 @@ struct SpecKernels {
   double compile_seconds = 0;
   bool from_cache = false;
   std::string lazy_why; /* why a lazily built module (phi_am_spec, phi_d_spec) is unavailable */
-  ~SpecKernels() { if (lib) cudaLibraryUnload(lib); if (libm) cudaLibraryUnload(libm); if (libd) cudaLibraryUnload(libd); }
+  ~SpecKernels() { if (lib) cudaLibraryUnload(lib); if (libm) cudaLibraryUnload(libm); if (libd) cudaLibraryUnload(libd); if (libtm) cudaLibraryUnload(libtm); }
 };
 
 obs::SpecOptions spec_default_options() {
@@ -450,6 +456,102 @@ bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double*
     void* args[] = {&p, &q};
     const cudaError_t e = cudaLaunchKernel((const void*)k.km, dim3(grid), dim3(32 * MW), args, smem, c.stream);
     if (e != cudaSuccess) throw CudaError(std::string("phi_am_spec: ") + cudaGetErrorString(e));
+    c.launches++;
+  }
+  return true;
+}
+
+/* out(term(slot), c) = sum over the J row groups of partial[(j * nslots + slot) * 64 + c], fixed order */
+__global__ void phi_tm_reduce_kernel(const double* __restrict__ partial, int J, int nslots, const int* __restrict__ slot_term, int ncols,
+                                     unsigned long long K, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x; /* one thread per (slot, column) */
+  if (idx >= nslots * 64) return;
+  const int i = idx >> 6, c = idx & 63;
+  const int t = slot_term[i];
+  if (t < 0 || c >= ncols) return;
+  double s = 0.0;
+  for (int j = 0; j < J; ++j) s += partial[((size_t)j * nslots + i) * 64 + c];
+  out[(unsigned long long)t + (unsigned long long)c * K] = s;
+}
+
+/* rows [0, N) of `ncols` columns into a buffer of leading dimension ld whose pad rows are zero (the tensor-core kernel
+ * multiplies pad rows by Phi = 0: they must be finite) */
+__global__ void pad_columns_kernel(const double* __restrict__ A, unsigned long long lda, unsigned long long N, unsigned long long ld, int ncols,
+                                   double* __restrict__ out) {
+  const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ld * (unsigned long long)ncols) return;
+  const unsigned long long n = idx % ld, c = idx / ld;
+  out[idx] = n < N ? A[n + c * lda] : 0.0;
+}
+
+/* Phi^T . A for C >= 8 columns as dense contractions on the FP64 tensor cores (phi_tm_spec, 64 columns per launch).
+ * pl.prog = the G = types * 8 program with streams of <= 32 terms.  out: K x C, column-major (local sums: the caller
+ * adds the ranks).  false: not available (module build failed, geometry) -- the caller runs the column loop. */
+bool launch_phi_tm_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, int types, const double* A, u64 lda, u64 C, double* out) {
+  const DevProgram& pr = *pl.prog;
+  const u64 K = pr.host.K;
+  if (K == 0 || C == 0) return true;
+  if (pl.cols->nload != pl.cols->ncol || pl.cols->has_ops || pl.N >= (1ull << 31)) return false;
+  if (pl.N == 0) { launch_fill(c, out, K * C, 0.0); return true; }
+  if (k.tm_state == 0) {
+    k.tm_state = -1;
+    obs::SpecSource S = obs::generate_tmat(pr.host, types, k.opt);
+    if (!S.ok) { k.lazy_why = "phi_tm_spec: " + S.why; return false; }
+    try {
+      k.libtm = spec_load_library(c, S.src, false, nullptr, nullptr);
+      OB_CUDA(cudaLibraryGetKernel(&k.ktm, k.libtm, "phi_tm_spec"));
+    } catch (const std::exception& ex) {
+      k.lazy_why = std::string("phi_tm_spec: ") + ex.what();
+      return false;
+    }
+    k.tm_maxcols = S.maxcols_t;
+    k.tm_state = 1;
+  }
+  if (k.tm_state != 1) return false;
+  constexpr int TR = 64, W = obs::kTmWarps, T = obs::kTmTerms, PS = 36, RS = 68, NP = 4;
+  obs::SpecParams p{};
+  spec_fill(p, pl, TR);
+  obs::TMatParams q{};
+  p.off_flags = 128;
+  q.off_park = 128 + 256;
+  p.off_tile = q.off_park + (unsigned)(W * T * PS * 8);
+  q.off_r = (unsigned)((k.tm_maxcols + 1) * TR * 8);
+  p.tile_doubles = (unsigned)((k.tm_maxcols + 1) * TR + 64 * RS);
+  const size_t stage_bytes = (size_t)p.tile_doubles * 8;
+  const size_t room = c.smem_optin > p.off_tile ? c.smem_optin - p.off_tile : 0;
+  p.nstage = (int)std::min<size_t>({(size_t)4, room / stage_bytes, (size_t)8});
+  if (p.nstage < 1) return false;
+  const size_t smem = p.off_tile + (size_t)p.nstage * stage_bytes;
+  const int J = std::max(1, std::min(p.ntiles, c.sms / types));
+  const int grid = J * types;
+  const int nslots = (int)pr.host.nslots();
+  const u64 ld = ((pl.N + 255) / 256) * 256;
+  q.partial = k.tm_partial.ensure((size_t)J * nslots * 64);
+  q.nslots = nslots;
+  if (smem > k.smem_tm_set) {
+    OB_CUDA(cudaFuncSetAttribute((const void*)k.ktm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k.smem_tm_set = smem;
+  }
+  for (u64 c0 = 0; c0 < C; c0 += 64) {
+    const int nc = (int)std::min<u64>(64, C - c0);
+    /* the tile reads whole 64-row blocks of every column: stage unpadded / unaligned callers into a zero-padded copy */
+    const double* Ac = A + c0 * lda;
+    u64 ldc = lda;
+    if (lda < ld || (reinterpret_cast<uintptr_t>(Ac) & 15u) || (lda & 1u)) {
+      k.tm_stage.ensure(ld * 64);
+      const u64 n = ld * (u64)nc;
+      pad_columns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(Ac, lda, pl.N, ld, nc, k.tm_stage.p);
+      c.launches++;
+      Ac = k.tm_stage.p; ldc = ld;
+    }
+    q.A = Ac; q.lda = ldc; q.ncols = nc;
+    void* args[] = {&p, &q};
+    const cudaError_t e = cudaLaunchKernel((const void*)k.ktm, dim3(grid), dim3(32 * (W + NP)), args, smem, c.stream);
+    if (e != cudaSuccess) throw CudaError(std::string("phi_tm_spec: ") + cudaGetErrorString(e));
+    c.launches++;
+    phi_tm_reduce_kernel<<<(nslots * 64 + 255) / 256, 256, 0, c.stream>>>(q.partial, J, nslots, pr.slot_term.p, nc, K, out + c0 * K);
+    const cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) throw CudaError(std::string("phi_tm_reduce_kernel: ") + cudaGetErrorString(e2));
     c.launches++;
   }
   return true;

@@ -265,6 +265,14 @@ def test_multi_rhs_tensor_core_kernel(spec, oracle, N, K, C):
     obg = spec.outerbase(omg, x)
     assert relerr(obg.sqmm(t2, np.abs(A)), o["ob"].sqmm(t2, np.abs(A))) < 1e-9
     assert relerr(obg.matmul(t2, A[:, :3]), o["ob"].matmul(t2, A[:, :3])) < 1e-9  # fewer than 8 columns: vector kernels
+    # the transpose, tprodmm_(mat) (linalg.cpp:583-637), contracted over the rows on the tensor cores (phi_tm_spec)
+    R = np.asfortranarray(rng.normal(size=(N, C)))
+    n0 = spec.launch_count()
+    got = spec.tprodmm(terms, R, o["bm"], o["bs"], o["kp"])
+    assert relerr(got, o["ob"].tmatmul(terms, R)) < MATVEC_TOL
+    assert spec.launch_count() - n0 <= 3 * ((C + 63) // 64)  # (pad copy +) one tensor-core launch + reduce per 64 columns
+    assert relerr(obg.sqtmmm(t2, np.abs(R)), o["ob"].sqtmmm(t2, np.abs(R))) < 1e-9
+    assert relerr(obg.tmatmul(t2, R[:, :3]), o["ob"].tmatmul(t2, R[:, :3])) < 1e-9
 
 
 def test_host_pointer_calls_overlap_their_transfers(spec):
