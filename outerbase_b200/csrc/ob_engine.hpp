@@ -630,6 +630,8 @@ struct OuterBase {
   }
   void tmm_mat(int sq, const u64* terms, u64 K, const double* A, u64 C, double* out) {
     tmpN2.ensure(ld * C);
+    /* pad rows must be finite: the tensor-core kernel multiplies them by Phi = 0 */
+    if (N < ld) OB_CUDA(cudaMemsetAsync(tmpN2.p, 0, ld * C * sizeof(double), ctx.stream));
     for (u64 c = 0; c < C; ++c)
       if (N) OB_CUDA(cudaMemcpyAsync(tmpN2.p + c * ld, A + c * N, N * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
     tmpK.ensure(K * C);
