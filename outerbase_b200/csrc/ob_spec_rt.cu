@@ -278,7 +278,11 @@ static void spec_launch(Ctx& c, cudaKernel_t kern, size_t& smem_set, int grid, i
 
 /* shared-memory layout: 16 mbarriers | coefficient copy (Phi a) | nstage tiles of (ncol + extra) columns */
 struct SpecGeom { int nstage = 0; unsigned off_vec = 0, off_tile = 0, tile_doubles = 0; size_t smem = 0; };
-static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t vec_bytes, int want_stages) {
+/* `group` = consumer groups that take the tiles round-robin.  The stage count is a multiple of it, so that every
+ * round of one stage goes to the SAME group: a group that met a stage of another group's could test its full
+ * barrier two phases late, and an mbarrier parity wait cannot tell phase r from phase r + 2 (seen as wrong rows /
+ * a launch failure once in a few runs with 4 groups on 5 or 6 stages). */
+static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t vec_bytes, int want_stages, int group = 1) {
   SpecGeom g;
   g.off_vec = 128 + 256; /* 16 mbarriers | 256 square flags | ... */
   g.off_tile = (unsigned)(g.off_vec + vec_bytes);
@@ -286,6 +290,7 @@ static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t
   const size_t tile_bytes = (size_t)g.tile_doubles * 8;
   const size_t room = c.smem_optin > g.off_tile ? c.smem_optin - g.off_tile : 0;
   g.nstage = (int)std::min<size_t>({(size_t)want_stages, room / std::max<size_t>(tile_bytes, 1), (size_t)8});
+  g.nstage -= g.nstage % std::max(group, 1);
   g.smem = g.off_tile + (size_t)g.nstage * tile_bytes;
   return g;
 }
@@ -295,7 +300,7 @@ static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t
 obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, size_t nslots) {
   for (;;) {
     const size_t vec = std::max<size_t>(((nslots * 8 + 127) / 128) * 128, 8 * 32 * (size_t)(o.qa * o.tga + o.np));
-    if (spec_geometry(c, ncol, 1, 32 * o.ra * o.qa, vec, 8).nstage >= o.tga) break;
+    if (spec_geometry(c, ncol, 1, 32 * o.ra * o.qa, vec, 8, o.tga).nstage >= o.tga) break;
     if (o.tga > 1) --o.tga;
     else if (o.qa > 1) o.qa /= 2;
     else if (o.ra > 1) o.ra /= 2;
@@ -307,9 +312,7 @@ obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, 
 
 bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol) {
   if (ncol + 2 > 256) return false; /* one square flag per tile column in a 256-byte block */
-  /* a consumer group must never be a whole round of stages ahead of the producer (mbarrier parity
-   * would alias): tiles in work at once <= stages */
-  return spec_geometry(c, ncol, 1, k.tr_a, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (k.opt.qa * k.opt.tga + k.opt.np)), 8).nstage >= k.opt.tga &&
+  return spec_geometry(c, ncol, 1, k.tr_a, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (k.opt.qa * k.opt.tga + k.opt.np)), 8, k.opt.tga).nstage >= k.opt.tga &&
          spec_geometry(c, k.maxcols_t, 2, k.tr_t, 0, 8).nstage >= 1;
 }
 
@@ -320,7 +323,7 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
   /* the coefficient copy doubles as the scratch of the final residual reduction (one double per thread) */
-  const SpecGeom g = spec_geometry(c, p.ncol, 1, TR, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (warps + k.opt.np)), k.opt.tga + 2);
+  const SpecGeom g = spec_geometry(c, p.ncol, 1, TR, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (warps + k.opt.np)), std::max(2 * k.opt.tga, 3), k.opt.tga);
   if (g.nstage < k.opt.tga) throw std::logic_error("specialised Phi a does not fit in shared memory");
   p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles; p.off_flags = 128;
   p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;
@@ -603,8 +606,9 @@ bool launch_phi_d_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double* 
   p.tile_doubles = (unsigned)((p.ncol + 1) * TR);
   const size_t tile_bytes = (size_t)p.tile_doubles * 8;
   const size_t room = c.smem_optin > p.off_tile ? c.smem_optin - p.off_tile : 0;
-  p.nstage = (int)std::min<size_t>({(size_t)k.opt.tgd + 2, room / tile_bytes, (size_t)8});
-  if (p.nstage < k.opt.tgd) return false; /* tiles in work at once <= stages (mbarrier parity) */
+  p.nstage = (int)std::min<size_t>({(size_t)std::max(2 * k.opt.tgd, 3), room / tile_bytes, (size_t)8});
+  p.nstage -= p.nstage % k.opt.tgd; /* every round of a stage to the same consumer group: see spec_geometry */
+  if (p.nstage < k.opt.tgd) return false;
   const size_t smem = p.off_tile + (size_t)p.nstage * tile_bytes;
   p.a = a;
   const int grid = std::max(1, std::min(p.ntiles, c.sms));
