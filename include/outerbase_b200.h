@@ -188,7 +188,11 @@ int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uin
  * on by default (same value on every rank; a rank whose module fails to build makes all ranks fall
  * back to the per-hyper products together); "device_cg" 1|0 (env OB_DEVICE_CG) -- lpdf::optcg
  * (src/fit.cpp:37-96) on lpdfvec(logpr_gauss, loglik_gauss) keeps every K-vector and scalar of the
- * loop in HBM (the host reads one stop flag per iteration); 0 = the host loop of round 1. */
+ * loop in HBM (the host reads one stop flag per iteration); 0 = the host loop of round 1;
+ * "overlap" 1|0 (env OB_OVERLAP) -- ob_outerbase_mm / _tmm on host buffers of 2^17 rows or more overlap
+ * the transfer with the kernel (page-locked result written by the kernel, input vector streamed in
+ * on a second stream); 0 = staged copies -- needed under tools that serialise kernels and copies
+ * (ncu), where the kernel would wait for rows that cannot arrive (it traps after 20 s). */
 int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
 int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
 /* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */
@@ -255,14 +259,21 @@ int ob_getm(ob_ctx* ctx, double* out, const uint64_t* terms, uint64_t K, uint64_
 /* ------------------------------------------------------------------ lpdf family
  * loglik_gauss  src/lpdfs/loglik_gauss.cpp:41-179   (device)
  * logpr_gauss   src/lpdfs/logpr_gauss.cpp:41-145    (K-vectors)
- * lpdfvec       src/fit.cpp:174-267,310-428,557-607 (diag-Hessian branch)
- * lpdf::optcg   src/fit.cpp:37-96 ; paralpdf :133 ; paralpdf_grad :146. */
+ * loglik_std    src/lpdfs/loglik_std.cpp:41-203     (device; full Hessian = tensor-core Phi^T Phi)
+ * lpdfvec       src/fit.cpp:174-301,310-428,503-612 (diagonal and full-Hessian branches)
+ * lpdf::optcg   src/fit.cpp:37-96 ; optnewton :98-131 ; paralpdf :133 ; paralpdf_grad :146. */
 int ob_loglik_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K,
                            const double* y, const double* x, uint64_t N, ob_lpdf** out);
 int ob_logpr_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K, ob_lpdf** out);
 /* new(loglik_gda, om, terms, y, x) -- src/lpdfs/loglik_gda.cpp:47-239, src/interfaceR.cpp:745-750: the stage-1
  * likelihood of obfit (R/fitting.R:84), two parameters (noisescale, lik.coeffscale); flag "dodiag" = doda. */
 int ob_loglik_gda_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K,
+                         const double* y, const double* x, uint64_t N, ob_lpdf** out);
+/* new(loglik_std, om, terms, y, x) -- src/lpdfs/loglik_std.cpp:41-59, src/interfaceR.cpp:733-737: loglik_gauss's model
+ * with the K x K Hessian (hess / hessgradhyp / hessgradpara), what lpdf::optnewton needs.  The reference holds the
+ * explicit N x K basis and its N x K x H gradient cube (getmge_, broken for row-chunked bases: linalg.cpp:788-810);
+ * here values and gradients come from the implicit products and only the Hessians touch explicit matrices. */
+int ob_loglik_std_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K,
                          const double* y, const double* x, uint64_t N, ob_lpdf** out);
 /* new(lpdfvec, a, b): a is child 0 (grad/gradhyp are sized from it, fit.cpp:338-343). */
 int ob_lpdfvec_create(ob_lpdf* a, ob_lpdf* b, ob_lpdf** out);
@@ -273,24 +284,32 @@ int ob_lpdf_updateom(ob_lpdf* l);
 int ob_lpdf_updatepara(ob_lpdf* l, const double* para, uint64_t npara);
 int ob_lpdf_updateterms(ob_lpdf* l, const uint64_t* terms, uint64_t K);
 int ob_lpdf_optcg(ob_lpdf* l, double tol, uint64_t maxepch);
+/* lpdf::optnewton, src/fit.cpp:98-131: one Newton step coeff += solve(hess, grad); sets fullhess. */
+int ob_lpdf_optnewton(ob_lpdf* l);
 int ob_lpdf_hessmult(ob_lpdf* l, const double* g, double* out /* K */);
+/* hess / hessgradhyp / hessgradpara (fit.h:86-88): K x K, K x K x H, K x K x npara column-major; an object without a
+ * full Hessian (loglik_gauss, loglik_gda) returns n = 0 as the reference returns empty matrices. */
+int ob_lpdf_hess(ob_lpdf* l, double* out /* K x K */, uint64_t* n);
+int ob_lpdf_hessgradhyp(ob_lpdf* l, double* out /* K x K x H */, uint64_t* n);
+int ob_lpdf_hessgradpara(ob_lpdf* l, double* out /* K x K x npara */, uint64_t* n);
 int ob_lpdf_diaghess(ob_lpdf* l, double* out /* K */);
 int ob_lpdf_diaghessgradhyp(ob_lpdf* l, double* out /* K x H */);
 int ob_lpdf_diaghessgradpara(ob_lpdf* l, double* out /* K x npara */);
 int ob_lpdf_paralpdf(ob_lpdf* l, const double* para, uint64_t npara, double* out);
 int ob_lpdf_paralpdf_grad(ob_lpdf* l, const double* para, uint64_t npara, double* out);
 /* flags: which in {"compute_val","compute_grad","compute_gradhyp","compute_gradpara",
- * "domarg"} -- the C++ member names (NOT the swapped R names, interfaceR.cpp:700-701). */
+ * "domarg", "fullhess"} -- the C++ member names (NOT the swapped R names, interfaceR.cpp:700-701). */
 int ob_lpdf_set_flag(ob_lpdf* l, const char* which, int value);
 int ob_lpdf_sizes(ob_lpdf* l, uint64_t* nterms, uint64_t* npara, uint64_t* nhyp, uint64_t* nrow);
 /* which in {"val"(1),"grad"(K),"gradhyp"(H),"gradpara"(npara),"coeff"(K),"para"(npara),
  * "yhat"(N, loglik_gauss),"coeffsd"(K, logpr_gauss),"totdiaghess"(K),
- * "cg_iters"(1, iterations the last optcg ran)}. */
+ * "tothess"(K x K, after a full-Hessian build), "cg_iters"(1, iterations the last optcg ran)}. */
 int ob_lpdf_get(ob_lpdf* l, const char* which, double* out, uint64_t* n);
 /* set coeff (warm start, fit.cpp:45-48 keeps coeff across optcg calls). */
 int ob_lpdf_set_coeff(ob_lpdf* l, const double* coeff, uint64_t K);
 
-/* predictor(lpdf) / pred_gauss: src/lpdfs/loglik_gauss.cpp:196-227 */
+/* predictor(lpdf) / pred_gauss: src/lpdfs/loglik_gauss.cpp:196-227 ; pred_gda: loglik_gda.cpp:249-283 ;
+ * predr_std: loglik_std.cpp:219-257 */
 int ob_predictor_create(ob_lpdf* loglik, ob_predictor** out);
 int ob_predictor_destroy(ob_predictor* p);
 int ob_predictor_update(ob_predictor* p, const double* x, uint64_t N);

@@ -1064,6 +1064,29 @@ mat outerbase::getbase(u64 dim) const { /* :634-639 */
   return out;
 }
 mat outerbase::getmat(const umat& terms) const { mat o; getm_(o, terms, basemat, basescale, knotptst, lv()); return o; }
+std::vector<mat> outerbase::getmat_gradhyp(const umat& terms) const { /* :663-669 ; dogetmge_ linalg.cpp:741-750 ; getmge_ :819-821 */
+  const u64 N = basemat.nr, K = terms.nr, H = gest.size() - 1;
+  std::vector<mat> outge(H, mat(N, K));
+  vec tempalt(N);
+  for (u64 k = 0; k < K; ++k)
+    for (u64 l = 0; l < H; ++l) {
+      std::fill(tempalt.begin(), tempalt.end(), 1.0);
+      for (u64 m = 0; m < terms.nc; ++m)
+        if (terms(k, m) > 0 && m != hypmatch[l]) {
+          const double* c = basemat.col(knotptst[m] + terms(k, m));
+          for (u64 i = 0; i < N; ++i) tempalt[i] *= c[i];
+        }
+      const double* g = basemat_gradhyp.col(gest[l] + terms(k, hypmatch[l]));
+      double* o = outge[l].col(k);
+      for (u64 i = 0; i < N; ++i) o[i] = tempalt[i] * g[i];
+    }
+  for (u64 l = 0; l < H; ++l)
+    for (u64 k = 0; k < K; ++k) {
+      double* o = outge[l].col(k);
+      for (u64 i = 0; i < N; ++i) o[i] *= basescale[i];
+    }
+  return outge;
+}
 void outerbase::mm(vec& out, const umat& terms, const vec& a) const { prodmm_(out, terms, a, basemat, basescale, knotptst, lv()); }
 void outerbase::tmm(vec& out, const umat& terms, const vec& a) const { tprodmm_(out, terms, a, basemat, basescale, knotptst, lv()); }
 void outerbase::mm_gradhyp(vec& out, mat& outge, const umat& terms, const vec& a) const {
@@ -1121,6 +1144,82 @@ vec lpdf::paralpdf_grad(const vec& parap) const { /* fit.cpp:146-157 */
   if (npara != parap.size()) return out;
   for (size_t l = 0; l < parap.size(); ++l) out[l] -= (parap[l] - para0[l]) / paravar[l];
   return out;
+}
+
+/* ---- small dense algebra in the order of the BLAS / LAPACK stand-ins of oracle/arma_shim (netlib reference BLAS:
+ * every output element is one left-to-right sum; solve / inv: elimination with partial pivoting) ---- */
+static mat dense_mul(const mat& A, const mat& B) { /* dgemm('N','N') / dgemv('N'): axpy sweeps, exact zeros of B skipped */
+  mat C(A.nr, B.nc);
+  for (u64 j = 0; j < B.nc; ++j)
+    for (u64 l = 0; l < A.nc; ++l) {
+      const double t = B(l, j);
+      if (t == 0.0) continue;
+      double* c = C.col(j);
+      const double* a = A.col(l);
+      for (u64 i = 0; i < A.nr; ++i) c[i] += t * a[i];
+    }
+  return C;
+}
+static vec dense_mul(const mat& A, const vec& b) {
+  vec c(A.nr, 0.0);
+  for (u64 l = 0; l < A.nc; ++l) {
+    if (b[l] == 0.0) continue;
+    const double* a = A.col(l);
+    for (u64 i = 0; i < A.nr; ++i) c[i] += b[l] * a[i];
+  }
+  return c;
+}
+static mat dense_tmul(const mat& A, const mat& B) { /* A^T B, dgemm('T','N'): one sequential dot per element */
+  mat C(A.nc, B.nc);
+  for (u64 j = 0; j < B.nc; ++j)
+    for (u64 i = 0; i < A.nc; ++i) C(i, j) = dot_seq(A.col(i), B.col(j), A.nr);
+  return C;
+}
+static mat dense_solve(const mat& A, const mat& B) {
+  if (A.nr != A.nc || A.nr != B.nr) throw std::invalid_argument("solve(): incompatible dimensions");
+  const u64 n = A.nr, m = B.nc;
+  mat L = A, X = B;
+  for (u64 k = 0; k < n; ++k) {
+    u64 p = k;
+    for (u64 i = k + 1; i < n; ++i) if (std::abs(L(i, k)) > std::abs(L(p, k))) p = i;
+    if (L(p, k) == 0.0) throw std::runtime_error("solve(): solution not found");
+    if (p != k) { for (u64 j = 0; j < n; ++j) std::swap(L(k, j), L(p, j)); for (u64 j = 0; j < m; ++j) std::swap(X(k, j), X(p, j)); }
+    for (u64 i = k + 1; i < n; ++i) {
+      const double f = L(i, k) / L(k, k);
+      if (f == 0.0) continue;
+      for (u64 j = k; j < n; ++j) L(i, j) -= f * L(k, j);
+      for (u64 j = 0; j < m; ++j) X(i, j) -= f * X(k, j);
+    }
+  }
+  for (u64 j = 0; j < m; ++j)
+    for (u64 ii = n; ii-- > 0;) {
+      double sacc = X(ii, j);
+      for (u64 c = ii + 1; c < n; ++c) sacc -= L(ii, c) * X(c, j);
+      X(ii, j) = sacc / L(ii, ii);
+    }
+  return X;
+}
+static mat dense_inv(const mat& A) {
+  mat I(A.nr, A.nr);
+  for (u64 i = 0; i < A.nr; ++i) I(i, i) = 1.0;
+  return dense_solve(A, I);
+}
+
+void lpdf::optnewton() { /* fit.cpp:98-131: one Newton step on the full Hessian */
+  fullhess = true;
+  compute_val = true; compute_grad = true; compute_gradhyp = false; compute_gradpara = false;
+  if (coeff.size() != nterms) coeff.assign(nterms, 0.0);
+  update(vec(coeff));
+  mat h = hess();
+  vec r = grad;
+  if (!all_finite(h.a) && !all_finite(r)) { val = -std::numeric_limits<double>::infinity(); return; }
+  mat rm(r.size(), 1);
+  rm.a = r;
+  const mat step = dense_solve(h, rm);
+  for (u64 i = 0; i < coeff.size(); ++i) coeff[i] += step.a[i];
+  compute_gradhyp = true; compute_gradpara = true;
+  update(vec(coeff));
+  compute_gradhyp = false; compute_gradpara = false;
 }
 
 void lpdf::optcg(double tol, unsigned maxepch) { /* fit.cpp:37-96 */
@@ -1227,6 +1326,143 @@ mat logpr_gauss::diaghessgradpara() { /* :143-145 */
   mat o(coeffsd.size(), 1);
   for (u64 i = 0; i < o.nr; ++i) { const double s = coeffsd[i] * sca; o(i, 0) = -2. / (s * s); }
   return o;
+}
+
+mat logpr_gauss::hess() { /* :153-158 */
+  mat h(nterms, nterms);
+  for (u64 i = 0; i < nterms; ++i) { const double sd = coeffsd[i] * sca; h(i, i) = 1. / (sd * sd); }
+  return h;
+}
+std::vector<mat> logpr_gauss::hessgradhyp() { /* :165-173 */
+  std::vector<mat> o(coefflvarge.nc, mat(nterms, nterms));
+  for (u64 l = 0; l < coefflvarge.nc; ++l)
+    for (u64 i = 0; i < nterms; ++i) { const double sd = coeffsd[i] * sca; o[l](i, i) = -(coefflvarge(i, l) / (sd * sd)); }
+  return o;
+}
+std::vector<mat> logpr_gauss::hessgradpara() { /* :181-186 */
+  std::vector<mat> o(1, mat(nterms, nterms));
+  for (u64 i = 0; i < nterms; ++i) { const double sd = coeffsd[i] * sca; o[0](i, i) = -2. / (sd * sd); }
+  return o;
+}
+
+/* ---- loglik_std ---- */
+loglik_std::loglik_std(const outermod& om_, const umat& terms_, const vec& y_, const mat& x_)
+    : om(om_), ob(om_, x_, true), y(y_), x(x_) { /* :41-59 */
+  terms = terms_;
+  npara = 1;
+  basismat = ob.getmat(terms);
+  basismat_gradhyp = ob.getmat_gradhyp(terms);
+  para0 = {std::log(0.01 * arma_var(y.data(), y.size()))};
+  paravar = {1};
+  para = para0;
+  nterms = terms.nr;
+}
+void loglik_std::updateom() { /* :67-71 */
+  ob.build();
+  basismat = ob.getmat(terms);
+  basismat_gradhyp = ob.getmat_gradhyp(terms);
+}
+void loglik_std::updatepara(const vec& p) { para = p; } /* :78-80 */
+void loglik_std::updateterms(const umat& t) { /* :87-92 */
+  terms = t;
+  nterms = terms.nr;
+  basismat = ob.getmat(terms);
+  basismat_gradhyp = ob.getmat_gradhyp(terms);
+}
+void loglik_std::update(const vec& coeff_) { /* :100-123 */
+  coeff = coeff_;
+  const u64 N = y.size(), H = basismat_gradhyp.size();
+  yhat = dense_mul(basismat, coeff);
+  mat yhatge;
+  if (compute_gradhyp) {
+    yhatge.set_size(N, H);
+    for (u64 l = 0; l < H; ++l) {
+      const vec c = dense_mul(basismat_gradhyp[l], coeff);
+      std::copy(c.begin(), c.end(), yhatge.col(l));
+    }
+  }
+  const double e = std::exp(-para[0]);
+  vec residtemp(N), residtemp2(N);
+  for (u64 i = 0; i < N; ++i) { residtemp[i] = e * (yhat[i] - y[i]); residtemp2[i] = residtemp[i] * residtemp[i]; }
+  if (compute_val) val = -0.5 * accu2(residtemp2.data(), N) - double(N) * para[0];
+  if (compute_grad) {
+    for (u64 i = 0; i < N; ++i) residtemp[i] = (-e) * residtemp[i];
+    ob.tmm(grad, terms, residtemp);
+    if (compute_gradhyp) {
+      gradhyp.assign(H, 0.0);
+      for (u64 h = 0; h < H; ++h) gradhyp[h] = dot_seq(residtemp.data(), yhatge.col(h), N);
+    }
+    if (compute_gradpara) gradpara = {accu2(residtemp2.data(), N) - double(N)};
+  }
+}
+vec loglik_std::hessmult(const vec& g) { /* :130-133 */
+  const vec t = dense_mul(basismat, g);
+  vec lh(basismat.nc);
+  const double c = std::exp(-2 * para[0]);
+  for (u64 k = 0; k < lh.size(); ++k) lh[k] = c * dot_seq(basismat.col(k), t.data(), basismat.nr);
+  return lh;
+}
+static vec colsums_of_squares(const mat& B) { /* sum(square(B), 0): one two-accumulator sum per column */
+  vec lh(B.nc), t(B.nr);
+  for (u64 k = 0; k < B.nc; ++k) {
+    const double* c = B.col(k);
+    for (u64 i = 0; i < B.nr; ++i) t[i] = c[i] * c[i];
+    lh[k] = accu2(t.data(), B.nr);
+  }
+  return lh;
+}
+vec loglik_std::diaghess() { /* :140-143 */
+  vec lh = colsums_of_squares(basismat);
+  const double c = std::exp(-2 * para[0]);
+  for (double& v : lh) v = c * v;
+  return lh;
+}
+mat loglik_std::diaghessgradhyp() { /* :150-155 */
+  const u64 N = basismat.nr, K = basismat.nc, H = basismat_gradhyp.size();
+  mat lh(K, H);
+  vec t(N);
+  const double c = std::exp(-2 * para[0]);
+  for (u64 h = 0; h < H; ++h)
+    for (u64 k = 0; k < K; ++k) {
+      const double* b = basismat.col(k);
+      const double* g = basismat_gradhyp[h].col(k);
+      for (u64 i = 0; i < N; ++i) t[i] = g[i] * (2 * b[i]);
+      lh(k, h) = c * accu2(t.data(), N);
+    }
+  return lh;
+}
+mat loglik_std::diaghessgradpara() { /* :162-165 */
+  const vec lh = colsums_of_squares(basismat);
+  mat o(lh.size(), 1);
+  const double c = -2 * std::exp(-2 * para[0]);
+  for (u64 i = 0; i < lh.size(); ++i) o(i, 0) = c * lh[i];
+  return o;
+}
+mat loglik_std::hess() { /* :173-176 */
+  mat lh = dense_tmul(basismat, basismat);
+  const double c = std::exp(-2 * para[0]);
+  for (double& v : lh.a) v = c * v;
+  return lh;
+}
+std::vector<mat> loglik_std::hessgradhyp() { /* :183-195 */
+  const u64 K = basismat.nc;
+  std::vector<mat> o;
+  const double c = std::exp(-2 * para[0]);
+  for (const mat& G : basismat_gradhyp) {
+    mat S = dense_tmul(basismat, G);
+    for (double& v : S.a) v = c * v;
+    mat R(K, K);
+    for (u64 j = 0; j < K; ++j)
+      for (u64 i = 0; i < K; ++i) R(i, j) = S(i, j) + S(j, i);
+    o.push_back(std::move(R));
+  }
+  return o;
+}
+std::vector<mat> loglik_std::hessgradpara() { /* :202-206 */
+  mat lh = dense_tmul(basismat, basismat);
+  const double c = -2 * std::exp(-2 * para[0]);
+  for (double& v : lh.a) v = c * v;
+  return {lh};
 }
 
 /* ---- loglik_gauss ---- */
@@ -1457,7 +1693,7 @@ void lpdfvec::updateterms(const umat& t) { /* :237-244 */
   for (lpdf* l : lpdflist) { l->updateterms(t); nterms = l->nterms; }
   redohess = true;
 }
-void lpdfvec::buildhess() { /* :252-267 (diagonal branch) */
+void lpdfvec::buildhess() { /* :252-301 */
   if (redohess) {
     diaghessv = diaghess_();
     settotdiaghess(diaghessv);
@@ -1480,7 +1716,80 @@ void lpdfvec::buildhess() { /* :252-267 (diagonal branch) */
       }
     }
   }
+  if (redohess && fullhess) { /* :269-299 */
+    hessv = hess_();
+    settothess(hessv);
+    if (domargadj) {
+      hessgradhypv = hessgradhyp_();
+      hessgradparav = hessgradpara_();
+      const u64 K = hessv.nr;
+      vec heigval;
+      mat heigvec;
+      eig_sym_jacobi(heigval, heigvec, hessv);
+      mat hessi(K, K);
+      for (u64 j = 0; j < K; ++j)
+        for (u64 i = 0; i < K; ++i) hessi(i, j) = heigvec(j, i) / heigval[i];
+      hessi = dense_mul(heigvec, hessi);
+      vec t(K);
+      for (u64 i = 0; i < K; ++i) t[i] = std::log(heigval[i]);
+      val_margadj = -0.5 * accu2(t.data(), K);
+      vec tm(K * K);
+      gradhyp_margadj.assign(hessgradhypv.size(), 0.0);
+      for (u64 l = 0; l < hessgradhypv.size(); ++l) {
+        for (u64 i = 0; i < K * K; ++i) tm[i] = hessgradhypv[l].a[i] * hessi.a[i];
+        gradhyp_margadj[l] = -0.5 * accu2(tm.data(), K * K);
+      }
+      gradpara_margadj.assign(hessgradparav.size(), 0.0);
+      for (u64 l = 0; l < hessgradparav.size(); ++l) {
+        for (u64 i = 0; i < K * K; ++i) tm[i] = hessgradparav[l].a[i] * hessi.a[i];
+        gradpara_margadj[l] = -0.5 * accu2(tm.data(), K * K);
+      }
+    }
+  }
   redohess = false;
+}
+void lpdfvec::settothess(const mat& h) { /* :609-612 */
+  tothess = h;
+  for (lpdf* l : lpdflist) l->settothess(h);
+}
+mat lpdfvec::hess_() { /* :503-512 */
+  mat out;
+  u64 cnt = 0;
+  for (lpdf* l : lpdflist) {
+    mat h = l->hess();
+    if (cnt == 0) out = h;
+    else {
+      if (h.a.size() != out.a.size()) throw std::invalid_argument("addition: incompatible matrix dimensions");
+      for (u64 i = 0; i < out.a.size(); ++i) out.a[i] += h.a[i];
+    }
+    cnt++;
+  }
+  return out;
+}
+std::vector<mat> lpdfvec::hessgradhyp_() { /* :520-531 */
+  std::vector<mat> out;
+  u64 cnt = 0;
+  for (lpdf* l : lpdflist) {
+    std::vector<mat> h = l->hessgradhyp();
+    if (cnt == 0) out = h;
+    else {
+      if (h.size() != out.size()) throw std::invalid_argument("addition: incompatible cube dimensions");
+      for (u64 s = 0; s < out.size(); ++s)
+        for (u64 i = 0; i < out[s].a.size(); ++i) out[s].a[i] += h[s].a[i];
+    }
+    cnt++;
+  }
+  return out;
+}
+std::vector<mat> lpdfvec::hessgradpara_() { /* :539-549 */
+  const u64 K = lpdflist[0]->nterms;
+  std::vector<mat> out(para.size(), mat(K, K));
+  for (u64 c = 0; c < lpdflist.size(); ++c) {
+    std::vector<mat> h = lpdflist[c]->hessgradpara();
+    if (h.size() != paraend[c] + 1 - parasrt[c]) throw std::invalid_argument("copy into subcube: incompatible dimensions");
+    for (u64 j = 0; j < h.size(); ++j) out[parasrt[c] + j] = h[j];
+  }
+  return out;
 }
 void lpdfvec::update(const vec& coeff_) { /* :323-361 */
   coeff = coeff_;
@@ -1592,6 +1901,40 @@ vec pred_gauss::var() const { /* :223-227 */
   const double c = std::exp(2 * para[0]);
   for (double& v : o) v += c;
   return o;
+}
+
+/* ---- predr_std ---- */
+predr_std::predr_std(const loglik_std& loglik) : om(loglik.om), para(loglik.para), terms(loglik.terms) { /* :219-238 */
+  ob.reset(new outerbase(om, loglik.x, false));
+  nthreads = (int)loglik.ob.nthreads;
+  ob->nthreads = nthreads;
+  coeff = loglik.coeff;
+  basismat = ob->getmat(terms);
+  const u64 K = coeff.size();
+  if (!loglik.didnotothess) {
+    if (loglik.didfulltothess) coeffcov = dense_inv(loglik.tothess);
+    else {
+      coeffcov = mat(K, K);
+      /* as written in the reference (:229): the diagonal of the total Hessian itself, not its inverse */
+      for (u64 i = 0; i < K; ++i) coeffcov(i, i) = loglik.totdiaghess[i];
+    }
+  } else coeffcov = mat(K, K);
+}
+void predr_std::update(const mat& x_) { /* :240-245 */
+  ob.reset(new outerbase(om, x_, false));
+  ob->nthreads = nthreads;
+  basismat = ob->getmat(terms);
+}
+vec predr_std::mean() const { return dense_mul(basismat, coeff); } /* :247-249 */
+vec predr_std::var() const { /* :251-257 */
+  mat adj = dense_mul(basismat, coeffcov);
+  for (u64 i = 0; i < adj.a.size(); ++i) adj.a[i] *= basismat.a[i];
+  vec out(adj.nr, 0.0);
+  if (adj.nc) std::copy(adj.col(0), adj.col(0) + adj.nr, out.begin());
+  for (u64 k = 1; k < adj.nc; ++k) { const double* c = adj.col(k); for (u64 i = 0; i < adj.nr; ++i) out[i] += c[i]; }
+  const double e2 = std::exp(2 * para[0]);
+  for (double& v : out) v += e2;
+  return out;
 }
 
 } // namespace orc

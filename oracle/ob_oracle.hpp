@@ -158,6 +158,10 @@ struct outerbase {
   loopvals lv() const { return {vertpl, chunksize, loopsize, (int)nthreads}; }
   mat getbase(u64 dim) const;                      /* :634-639 */
   mat getmat(const umat& terms) const;             /* :649-654 */
+  /* :663-669 -> getmge_ / dogetmge_, linalg.cpp:724-822.  One N x K slice per hyper-parameter.  The reference's
+   * row-chunked branch (vertpl, linalg.cpp:788-810) cannot work (dogetmge_ resizes the whole cube to one chunk and the
+   * chunk result is never copied back); the formula of the unchunked branch is used for every shape here. */
+  std::vector<mat> getmat_gradhyp(const umat& terms) const;
   void mm(vec& out, const umat& terms, const vec& a) const;   /* :677-680 */
   void tmm(vec& out, const umat& terms, const vec& a) const;  /* :700-703 */
   void mm_gradhyp(vec& out, mat& outge, const umat& terms, const vec& a) const;  /* :725-731 */
@@ -179,6 +183,7 @@ struct lpdf {
   vec grad, gradhyp, gradpara, para;
   umat terms;
   vec coeff, totdiaghess;
+  mat tothess;
   bool didfulltothess = false, didnotothess = true, fullhess = false;
   bool compute_val = true, compute_grad = true, compute_gradhyp = false, compute_gradpara = false;
   unsigned npara = 0, nterms = 0;
@@ -189,6 +194,7 @@ struct lpdf {
   virtual double paralpdf(const vec& parap) const;    /* fit.cpp:133-142 */
   virtual vec paralpdf_grad(const vec& parap) const;  /* fit.cpp:146-157 */
   virtual void optcg(double tol, unsigned maxepch);   /* fit.cpp:37-96 */
+  virtual void optnewton();                           /* fit.cpp:98-131 */
   virtual void updateom() {}
   virtual void updatepara(const vec&) {}
   virtual void updateterms(const umat&) {}
@@ -198,6 +204,10 @@ struct lpdf {
   virtual mat diaghessgradhyp() { return {}; }
   virtual mat diaghessgradpara() { return {}; }
   virtual void settotdiaghess(const vec& dh) { totdiaghess = dh; didfulltothess = false; didnotothess = false; }
+  virtual void settothess(const mat& h) { tothess = h; didfulltothess = true; didnotothess = false; } /* fit.h:81-85 */
+  virtual mat hess() { return {}; }
+  virtual std::vector<mat> hessgradhyp() { return {}; }  /* cube: one K x K slice per hyper-parameter */
+  virtual std::vector<mat> hessgradpara() { return {}; } /* one slice per parameter */
   virtual u64 nhyp() const { return 0; }
   virtual u64 nrow() const { return 0; }
 };
@@ -217,7 +227,35 @@ struct logpr_gauss : lpdf { /* src/lpdfs/logpr_gauss.cpp:41-145 */
   vec diaghess() override;
   mat diaghessgradhyp() override;
   mat diaghessgradpara() override;
+  mat hess() override;                      /* :153-158 */
+  std::vector<mat> hessgradhyp() override;  /* :165-173 */
+  std::vector<mat> hessgradpara() override; /* :181-186 */
   u64 nhyp() const override { return om.hypmatch.size(); }
+};
+
+struct loglik_std : lpdf { /* src/lpdfs/loglik_std.cpp:41-203, src/fit.h:182-211: the same model as loglik_gauss on the
+                             EXPLICIT basis matrix (N x K) and its hyper-gradient cube, with the full Hessian */
+  const outermod& om;
+  outerbase ob;
+  mat basismat;
+  std::vector<mat> basismat_gradhyp;
+  vec y, yhat;
+  mat x;
+  loglik_std(const outermod& om_, const umat& terms_, const vec& y_, const mat& x_);
+  void setnthreads(int) override {} /* not overridden in the reference: ob keeps its thread count */
+  void updateom() override;
+  void updatepara(const vec&) override;
+  void updateterms(const umat&) override;
+  void update(const vec& coeff_) override;
+  vec hessmult(const vec& g) override;
+  vec diaghess() override;
+  mat diaghessgradhyp() override;
+  mat diaghessgradpara() override;
+  mat hess() override;
+  std::vector<mat> hessgradhyp() override;
+  std::vector<mat> hessgradpara() override;
+  u64 nhyp() const override { return ob.n_hyp; }
+  u64 nrow() const override { return ob.n_row; }
 };
 
 struct loglik_gauss : lpdf { /* src/lpdfs/loglik_gauss.cpp:41-179 */
@@ -274,6 +312,8 @@ struct lpdfvec : lpdf { /* src/fit.h:93-148 ; src/fit.cpp:174-267,310-428,557-60
   bool domargadj = true;
   vec diaghessv;
   mat diaghessgradhypv, diaghessgradparav;
+  mat hessv;
+  std::vector<mat> hessgradhypv, hessgradparav;
   bool redohess = true;
   std::vector<lpdf*> lpdflist;
   std::vector<u64> parasrt, paraend;
@@ -288,6 +328,13 @@ struct lpdfvec : lpdf { /* src/fit.h:93-148 ; src/fit.cpp:174-267,310-428,557-60
   mat diaghessgradhyp() override { return diaghessgradhypv; }
   mat diaghessgradpara() override { return diaghessgradparav; }
   void settotdiaghess(const vec& dh) override;
+  void settothess(const mat& h) override;                           /* :609-612 */
+  mat hess() override { return hessv; }                              /* :436-438 */
+  std::vector<mat> hessgradhyp() override { return hessgradhypv; }   /* :446-448 */
+  std::vector<mat> hessgradpara() override { return hessgradparav; } /* :456-458 */
+  mat hess_();                       /* :503-512 */
+  std::vector<mat> hessgradhyp_();   /* :520-531 */
+  std::vector<mat> hessgradpara_();  /* :539-549 */
   double paralpdf(const vec& parap) const override;
   vec paralpdf_grad(const vec& parap) const override;
   void buildhess();
@@ -307,6 +354,21 @@ struct pred_gauss { /* src/lpdfs/loglik_gauss.cpp:196-227 */
   vec coeff, coeffvar;
   std::unique_ptr<outerbase> ob;
   pred_gauss(const loglik_gauss& loglik);
+  void update(const mat& x_);
+  vec mean() const;
+  vec var() const;
+};
+
+struct predr_std { /* src/lpdfs/loglik_std.cpp:219-255 */
+  const outermod& om;
+  vec para;
+  umat terms;
+  mat basismat;
+  int nthreads = 0;
+  vec coeff;
+  mat coeffcov;
+  std::unique_ptr<outerbase> ob;
+  predr_std(const loglik_std& loglik);
   void update(const mat& x_);
   vec mean() const;
   vec var() const;

@@ -36,7 +36,7 @@ struct orc_lpdf {
   std::unique_ptr<lpdf> p;
   int kind; /* 0 loglik_gauss, 1 logpr_gauss, 2 lpdfvec */
 };
-struct orc_predictor { std::unique_ptr<pred_gauss> p; std::unique_ptr<pred_gda> pg; uint64_t d; };
+struct orc_predictor { std::unique_ptr<pred_gauss> p; std::unique_ptr<pred_gda> pg; std::unique_ptr<predr_std> ps; uint64_t d; };
 
 static umat to_umat(const uint64_t* t, uint64_t K, uint64_t d) {
   umat m(K, d);
@@ -396,6 +396,23 @@ int orc_loglik_gauss_create(orc_ctx*, orc_outermod* om, const uint64_t* terms, u
   *out = h;
   ORC_CATCH
 }
+int orc_loglik_std_create(orc_ctx*, orc_outermod* om, const uint64_t* terms, uint64_t K, const double* y,
+                          const double* x, uint64_t N, orc_lpdf** out) {
+  ORC_TRY
+  auto* h = new orc_lpdf();
+  h->kind = 3;
+  h->p.reset(new loglik_std(om->om, to_umat(terms, K, om->om.d), vec(y, y + N), to_mat(x, N, om->om.d)));
+  *out = h;
+  ORC_CATCH
+}
+static void put_cube(const std::vector<mat>& c, double* out, uint64_t* n) {
+  *n = 0;
+  for (const mat& m : c) { std::copy(m.a.begin(), m.a.end(), out + *n); *n += m.a.size(); }
+}
+int orc_lpdf_optnewton(orc_lpdf* l) { ORC_TRY l->p->optnewton(); ORC_CATCH }
+int orc_lpdf_hess(orc_lpdf* l, double* out, uint64_t* n) { ORC_TRY mat h = l->p->hess(); std::copy(h.a.begin(), h.a.end(), out); *n = h.a.size(); ORC_CATCH }
+int orc_lpdf_hessgradhyp(orc_lpdf* l, double* out, uint64_t* n) { ORC_TRY put_cube(l->p->hessgradhyp(), out, n); ORC_CATCH }
+int orc_lpdf_hessgradpara(orc_lpdf* l, double* out, uint64_t* n) { ORC_TRY put_cube(l->p->hessgradpara(), out, n); ORC_CATCH }
 int orc_loglik_gda_create(orc_ctx*, orc_outermod* om, const uint64_t* terms, uint64_t K, const double* y,
                           const double* x, uint64_t N, orc_lpdf** out) {
   ORC_TRY
@@ -450,6 +467,7 @@ int orc_lpdf_set_flag(orc_lpdf* l, const char* which, int value) {
   else if (w == "compute_grad") l->p->compute_grad = value;
   else if (w == "compute_gradhyp") l->p->compute_gradhyp = value;
   else if (w == "compute_gradpara") l->p->compute_gradpara = value;
+  else if (w == "fullhess") l->p->fullhess = value;
   else if (w == "domarg") {
     auto* v = dynamic_cast<lpdfvec*>(l->p.get());
     if (!v) throw std::invalid_argument("domarg is a field of lpdfvec");
@@ -476,11 +494,13 @@ int orc_lpdf_get(orc_lpdf* l, const char* which, double* out, uint64_t* n) {
   else if (w == "coeff") v = l->p->coeff;
   else if (w == "para") v = l->p->para;
   else if (w == "totdiaghess") v = l->p->totdiaghess;
+  else if (w == "tothess") v = l->p->tothess.a;
   else if (w == "cg_iters") v = {double(l->p->cg_iters)};
   else if (w == "yhat") {
     if (auto* g = dynamic_cast<loglik_gauss*>(l->p.get())) v = g->yhat;
     else if (auto* g2 = dynamic_cast<loglik_gda*>(l->p.get())) v = g2->yhat;
-    else throw std::invalid_argument("yhat is a field of loglik_gauss / loglik_gda");
+    else if (auto* g3 = dynamic_cast<loglik_std*>(l->p.get())) v = g3->yhat;
+    else throw std::invalid_argument("yhat is a field of loglik_gauss / loglik_gda / loglik_std");
   } else if (w == "coeffsd") {
     auto* g = dynamic_cast<logpr_gauss*>(l->p.get());
     if (!g) throw std::invalid_argument("coeffsd is a field of logpr_gauss");
@@ -497,15 +517,16 @@ int orc_predictor_create(orc_lpdf* loglik, orc_predictor** out) {
   auto* h = new orc_predictor();
   if (auto* g = dynamic_cast<loglik_gauss*>(loglik->p.get())) { h->p.reset(new pred_gauss(*g)); h->d = g->om.d; }
   else if (auto* g2 = dynamic_cast<loglik_gda*>(loglik->p.get())) { h->pg.reset(new pred_gda(*g2)); h->d = g2->om.d; }
+  else if (auto* g3 = dynamic_cast<loglik_std*>(loglik->p.get())) { h->ps.reset(new predr_std(*g3)); h->d = g3->om.d; }
   else { delete h; throw std::invalid_argument("cannot produce a predictor from this obj."); }
   *out = h;
   ORC_CATCH
 }
 int orc_predictor_destroy(orc_predictor* p) { delete p; return ORC_OK; }
 int orc_predictor_update(orc_predictor* p, const double* x, uint64_t N) {
-  ORC_TRY if (p->p) p->p->update(to_mat(x, N, p->d)); else p->pg->update(to_mat(x, N, p->d)); ORC_CATCH
+  ORC_TRY if (p->p) p->p->update(to_mat(x, N, p->d)); else if (p->pg) p->pg->update(to_mat(x, N, p->d)); else p->ps->update(to_mat(x, N, p->d)); ORC_CATCH
 }
-int orc_predictor_mean(orc_predictor* p, double* out) { ORC_TRY vec o = p->p ? p->p->mean() : p->pg->mean(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
-int orc_predictor_var(orc_predictor* p, double* out) { ORC_TRY vec o = p->p ? p->p->var() : p->pg->var(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
+int orc_predictor_mean(orc_predictor* p, double* out) { ORC_TRY vec o = p->p ? p->p->mean() : p->pg ? p->pg->mean() : p->ps->mean(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
+int orc_predictor_var(orc_predictor* p, double* out) { ORC_TRY vec o = p->p ? p->p->var() : p->pg ? p->pg->var() : p->ps->var(); std::copy(o.begin(), o.end(), out); ORC_CATCH }
 
 } // extern "C"

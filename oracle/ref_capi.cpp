@@ -450,6 +450,14 @@ int ref_loglik_gauss_create(ref_ctx*, ref_outermod* om, const uint64_t* terms, u
   *out = h;
   REF_CATCH
 }
+int ref_loglik_std_create(ref_ctx*, ref_outermod* om, const uint64_t* terms, uint64_t K, const double* y, const double* x, uint64_t N, ref_lpdf** out) {
+  REF_TRY
+  auto* h = new ref_lpdf();
+  auto* p = new counting<loglik_std>(om->om, to_umat(terms, K, om->om.d), to_vec(y, N), to_mat(x, N, om->om.d));
+  h->p.reset(p); h->hm = &p->hm_calls; h->kind = 4; h->nhyp = om->om.hyp.n_elem; h->nrow = N; h->d = om->om.d;
+  *out = h;
+  REF_CATCH
+}
 int ref_loglik_gda_create(ref_ctx*, ref_outermod* om, const uint64_t* terms, uint64_t K, const double* y, const double* x, uint64_t N, ref_lpdf** out) {
   REF_TRY
   auto* h = new ref_lpdf();
@@ -488,6 +496,10 @@ int ref_lpdf_optcg(ref_lpdf* l, double tol, uint64_t maxepch) {
   REF_CATCH
 }
 int ref_lpdf_optnewton(ref_lpdf* l) { REF_TRY l->p->optnewton(); REF_CATCH }
+static void put_cube(const cube& c, double* out, uint64_t* n) { *n = c.n_elem; std::copy(c.store.begin(), c.store.end(), out); }
+int ref_lpdf_hess(ref_lpdf* l, double* out, uint64_t* n) { REF_TRY mat h = l->p->hess(); *n = h.n_elem; put(h, out); REF_CATCH }
+int ref_lpdf_hessgradhyp(ref_lpdf* l, double* out, uint64_t* n) { REF_TRY put_cube(l->p->hessgradhyp(), out, n); REF_CATCH }
+int ref_lpdf_hessgradpara(ref_lpdf* l, double* out, uint64_t* n) { REF_TRY put_cube(l->p->hessgradpara(), out, n); REF_CATCH }
 int ref_lpdf_hessmult(ref_lpdf* l, const double* g, double* out) { REF_TRY put(l->p->hessmult(to_vec(g, l->p->nterms)), out); REF_CATCH }
 int ref_lpdf_diaghess(ref_lpdf* l, double* out) { REF_TRY put(l->p->diaghess(), out); REF_CATCH }
 int ref_lpdf_diaghessgradhyp(ref_lpdf* l, double* out) { REF_TRY put(l->p->diaghessgradhyp(), out); REF_CATCH }
@@ -501,6 +513,7 @@ int ref_lpdf_set_flag(ref_lpdf* l, const char* which, int value) {
   else if (w == "compute_grad") l->p->compute_grad = value;
   else if (w == "compute_gradhyp") l->p->compute_gradhyp = value;
   else if (w == "compute_gradpara") l->p->compute_gradpara = value;
+  else if (w == "fullhess") l->p->fullhess = value;
   else if (w == "domarg") {
     auto* v = dynamic_cast<lpdfvec*>(l->p.get());
     if (!v) throw std::invalid_argument("domarg is a field of lpdfvec");
@@ -527,11 +540,13 @@ int ref_lpdf_get(ref_lpdf* l, const char* which, double* out, uint64_t* n) {
   else if (w == "coeff") v = l->p->coeff;
   else if (w == "para") v = l->p->para;
   else if (w == "totdiaghess") v = l->p->totdiaghess;
+  else if (w == "tothess") { const mat& th = l->p->tothess; v.set_size(th.n_elem); std::copy(th.mem, th.mem + th.n_elem, v.mem); }
   else if (w == "cg_iters") v = vec({double(l->cg_iters)});
   else if (w == "yhat") {
     if (auto* g = dynamic_cast<loglik_gauss*>(l->p.get())) v = g->yhat;
     else if (auto* g2 = dynamic_cast<loglik_gda*>(l->p.get())) v = g2->yhat;
-    else throw std::invalid_argument("yhat is a field of loglik_gauss / loglik_gda");
+    else if (auto* g3 = dynamic_cast<loglik_std*>(l->p.get())) v = g3->yhat;
+    else throw std::invalid_argument("yhat is a field of loglik_gauss / loglik_gda / loglik_std");
   } else if (w == "coeffsd") {
     auto* g = dynamic_cast<logpr_gauss*>(l->p.get());
     if (!g) throw std::invalid_argument("coeffsd is a field of logpr_gauss");

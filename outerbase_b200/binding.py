@@ -201,6 +201,9 @@ class Library:
     def loglik_gda(self, om, terms, y, x):
         return loglik_gda(self, om, terms, y, x)
 
+    def loglik_std(self, om, terms, y, x):
+        return loglik_std(self, om, terms, y, x)
+
     def logpr_gauss(self, om, terms):
         return logpr_gauss(self, om, terms)
 
@@ -584,6 +587,8 @@ class lpdf(_Handle):
     coeff = property(lambda s: s._get("coeff"))
     para = property(lambda s: s._get("para"))
     totdiaghess = property(lambda s: s._get("totdiaghess"))
+    tothess = property(lambda s: (lambda v: v.reshape((int(round(v.size ** 0.5)),) * 2, order="F"))(s._get("tothess")))
+    fullhess = property(fset=lambda s, v: s._flag("fullhess", v))
     cg_iters = property(lambda s: int(s._get("cg_iters")[0]))
     # C++ member names; the R module swaps gradhyp/gradpara (interfaceR.cpp:700-701)
     compute_val = property(fset=lambda s, v: s._flag("compute_val", v))
@@ -612,9 +617,34 @@ class lpdf(_Handle):
     def optcg(self, tol, epoch):
         self._lib.call("lpdf_optcg", self._h, C.c_double(tol), _u(epoch))
 
+    def optnewton(self):
+        """lpdf$optnewton() -- src/fit.cpp:98-131, src/interfaceR.cpp:715."""
+        self._lib.call("lpdf_optnewton", self._h)
+
     def set_coeff(self, coeff):
         c = _f64(coeff)
         self._lib.call("lpdf_set_coeff", self._h, _p(c), _u(c.size))
+
+    def _cube(self, name, nslices):
+        k = self.nterms
+        out = np.empty((k, k, max(nslices, 1)), order="F")
+        n = C.c_uint64()
+        self._lib.call(name, self._h, _p(out), C.byref(n))
+        if n.value == 0:  # the reference returns an empty matrix / cube (fit.h:86-88)
+            return np.empty((0, 0, 0), order="F")
+        if n.value != k * k * nslices:
+            raise RuntimeError(f"{name}: {n.value} values for a {k} x {k} x {nslices} result")
+        return out[:, :, :nslices]
+
+    def hess(self):
+        h = self._cube("lpdf_hess", 1)
+        return h[:, :, 0] if h.size else np.empty((0, 0))
+
+    def hessgradhyp(self):
+        return self._cube("lpdf_hessgradhyp", self._sizes()[2])
+
+    def hessgradpara(self):
+        return self._cube("lpdf_hessgradpara", self._sizes()[1])
 
     def hessmult(self, g):
         g = _f64(g)
@@ -662,6 +692,20 @@ class loglik_gauss(lpdf):
         if x.shape[0] != y.size:
             raise ValueError("x and y dims do not align")
         lib.call("loglik_gauss_create", lib.ctx, om._h, _p(t), _u(t.shape[0]), _p(y), _p(x), _u(y.size), C.byref(self._h))
+
+    yhat = property(lambda s: s._get("yhat"))
+
+
+class loglik_std(lpdf):
+    """new(loglik_std, om, terms, y, x) -- src/lpdfs/loglik_std.cpp:41, src/interfaceR.cpp:733-737."""
+
+    def __init__(self, lib, om, terms, y, x):
+        super().__init__(lib)
+        self._om = om
+        t, y, x = _terms(terms), _f64(y), _f64(x)
+        if x.shape[0] != y.size:
+            raise ValueError("x and y dims do not align")
+        lib.call("loglik_std_create", lib.ctx, om._h, _p(t), _u(t.shape[0]), _p(y), _p(x), _u(y.size), C.byref(self._h))
 
     yhat = property(lambda s: s._get("yhat"))
 

@@ -26,7 +26,7 @@ struct ob_ctx { obd::Ctx c; explicit ob_ctx(int dev) : c(dev) {} };
 struct ob_outermod { obh::OuterMod om; };
 struct ob_outerbase { ob_ctx* ctx; std::unique_ptr<obe::OuterBase> ob; };
 struct ob_lpdf { ob_ctx* ctx; std::unique_ptr<obe::Lpdf> p; };
-struct ob_predictor { std::unique_ptr<obe::PredGauss> p; std::unique_ptr<obe::PredGda> pg; };
+struct ob_predictor { std::unique_ptr<obe::PredGauss> p; std::unique_ptr<obe::PredGda> pg; std::unique_ptr<obe::PredrStd> ps; };
 
 static void need(const void* p, const char* what) { if (!p) throw std::invalid_argument(std::string("null ") + what); }
 
@@ -254,6 +254,7 @@ int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value) {
   } else if (n == "spec_work") ctx->c.spec_work = value;
   else if (n == "dsweep") ctx->c.dsweep = value != 0;
   else if (n == "device_cg") ctx->c.device_cg = value != 0;
+  else if (n == "overlap") ctx->c.overlap = value != 0;
   else if (n == "p2p") ctx->c.p2p.enabled = value != 0; /* same value on every rank */
   else throw std::invalid_argument("unknown option " + n);
   OB_CATCH
@@ -400,6 +401,20 @@ int ob_loglik_gauss_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, 
   *out = h;
   OB_CATCH
 }
+int ob_loglik_std_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K, const double* y, const double* x,
+                         uint64_t N, ob_lpdf** out) {
+  OB_TRY
+  need(ctx, "ctx"); need(om, "om");
+  auto* h = new ob_lpdf();
+  h->ctx = ctx;
+  try { h->p.reset(new obe::LoglikStd(ctx->c, &om->om, terms, K, y, x, N)); } catch (...) { delete h; throw; }
+  *out = h;
+  OB_CATCH
+}
+int ob_lpdf_optnewton(ob_lpdf* l) { OB_TRY l->p->optnewton(); OB_CATCH }
+int ob_lpdf_hess(ob_lpdf* l, double* out, uint64_t* n) { OB_TRY auto o = l->p->hess(); std::copy(o.begin(), o.end(), out); *n = o.size(); OB_CATCH }
+int ob_lpdf_hessgradhyp(ob_lpdf* l, double* out, uint64_t* n) { OB_TRY auto o = l->p->hessgradhyp(); std::copy(o.begin(), o.end(), out); *n = o.size(); OB_CATCH }
+int ob_lpdf_hessgradpara(ob_lpdf* l, double* out, uint64_t* n) { OB_TRY auto o = l->p->hessgradpara(); std::copy(o.begin(), o.end(), out); *n = o.size(); OB_CATCH }
 int ob_loglik_gda_create(ob_ctx* ctx, ob_outermod* om, const uint64_t* terms, uint64_t K, const double* y, const double* x,
                          uint64_t N, ob_lpdf** out) {
   OB_TRY
@@ -453,6 +468,7 @@ int ob_lpdf_set_flag(ob_lpdf* l, const char* which, int value) {
   else if (w == "compute_grad") l->p->compute_grad = value;
   else if (w == "compute_gradhyp") l->p->compute_gradhyp = value;
   else if (w == "compute_gradpara") l->p->compute_gradpara = value;
+  else if (w == "fullhess") l->p->fullhess = value;
   else if (w == "domarg") {
     auto* v = dynamic_cast<obe::LpdfVec*>(l->p.get());
     if (!v) throw std::invalid_argument("domarg is a field of lpdfvec");
@@ -478,6 +494,7 @@ int ob_lpdf_get(ob_lpdf* l, const char* which, double* out, uint64_t* n) {
   else if (w == "coeff") v = l->p->coeff;
   else if (w == "para") v = l->p->para;
   else if (w == "totdiaghess") v = l->p->totdiaghess;
+  else if (w == "tothess") v = l->p->tothess;
   else if (w == "cg_iters") v = {double(l->p->cg_iters)};
   else if (w == "yhat") {
     if (auto* g = dynamic_cast<obe::LoglikGauss*>(l->p.get())) v = g->get_yhat();
@@ -498,7 +515,8 @@ int ob_predictor_create(ob_lpdf* loglik, ob_predictor** out) {
   OB_TRY
   auto* h = new ob_predictor();
   try {
-    if (auto* g = dynamic_cast<obe::LoglikGauss*>(loglik->p.get())) h->p.reset(new obe::PredGauss(*g));
+    if (auto* g3 = dynamic_cast<obe::LoglikStd*>(loglik->p.get())) h->ps.reset(new obe::PredrStd(*g3)); /* before its base class */
+    else if (auto* g = dynamic_cast<obe::LoglikGauss*>(loglik->p.get())) h->p.reset(new obe::PredGauss(*g));
     else if (auto* g2 = dynamic_cast<obe::LoglikGda*>(loglik->p.get())) h->pg.reset(new obe::PredGda(*g2));
     else throw std::invalid_argument("cannot produce a predictor from this obj.");
   } catch (...) { delete h; throw; }
@@ -506,8 +524,8 @@ int ob_predictor_create(ob_lpdf* loglik, ob_predictor** out) {
   OB_CATCH
 }
 int ob_predictor_destroy(ob_predictor* p) { OB_TRY delete p; OB_CATCH }
-int ob_predictor_update(ob_predictor* p, const double* x, uint64_t N) { OB_TRY if (p->p) p->p->update(x, N); else p->pg->update(x, N); OB_CATCH }
-int ob_predictor_mean(ob_predictor* p, double* out) { OB_TRY if (p->p) p->p->mean(out); else p->pg->mean(out); OB_CATCH }
-int ob_predictor_var(ob_predictor* p, double* out) { OB_TRY if (p->p) p->p->var(out); else p->pg->var(out); OB_CATCH }
+int ob_predictor_update(ob_predictor* p, const double* x, uint64_t N) { OB_TRY if (p->p) p->p->update(x, N); else if (p->pg) p->pg->update(x, N); else p->ps->update(x, N); OB_CATCH }
+int ob_predictor_mean(ob_predictor* p, double* out) { OB_TRY if (p->p) p->p->mean(out); else if (p->pg) p->pg->mean(out); else p->ps->mean(out); OB_CATCH }
+int ob_predictor_var(ob_predictor* p, double* out) { OB_TRY if (p->p) p->p->var(out); else if (p->pg) p->pg->var(out); else p->ps->var(out); OB_CATCH }
 
 } // extern "C"

@@ -98,6 +98,9 @@ struct Ctx {
   bool extra_done = false;
   /* lpdf::optcg with every K-vector in HBM (option "device_cg", env OB_DEVICE_CG; on by default) */
   bool device_cg = true;
+  /* host-pointer mm / tmm overlap their transfers with the kernel (option "overlap", env OB_OVERLAP; on by default).
+   * Off under tools that serialise kernels and copies (ncu): the kernel would wait for rows that cannot arrive. */
+  bool overlap = true;
   void fuse_allreduce(size_t n) { fused = false; fuse_n = p2p_ok(n) ? n : 0; }
   void allreduce_after(double* buf_dev, size_t n) {
     fuse_n = 0;
@@ -314,6 +317,7 @@ void launch_scaled_product(Ctx& c, double coef, const double* g, const double* w
 void launch_masked_add(Ctx& c, const double* a, const double* b, const unsigned char* mask, u64 n, double* out);
 /* elementwise helpers */
 void launch_fill(Ctx& c, double* p, u64 n, double v);
+void launch_rowdot(Ctx& c, const double* A, const double* B, u64 N, u64 K, u64 ld, double add, double* out);
 /* outge[:,h] (N) dotted with w (N) -> out[h], deterministic two-stage */
 void launch_dot_partials(Ctx& c, const double* a, const double* b, u64 n, double* partial, int* nblocks);
 

@@ -545,7 +545,7 @@ struct OuterBase {
   static constexpr u64 kOverlapRows = 1u << 17;
   void mm(int sq, const u64* terms, u64 K, const double* a, double* out) {
     tmpK.upload(a, K, ctx.stream);
-    if (N >= kOverlapRows)
+    if (ctx.overlap && N >= kOverlapRows)
       if (double* mapped = obd::Ctx::mapped_host_pointer(out)) {
         mm_dev(terms, K, sq, tmpK.p, mapped);
         ctx.sync();
@@ -559,7 +559,7 @@ struct OuterBase {
     tmpN.ensure(ld);
     tmpK.ensure(K);
     bool done = false;
-    if (N >= kOverlapRows && N < (1ull << 31)) {
+    if (ctx.overlap && N >= kOverlapRows && N < (1ull << 31)) {
       const unsigned* ready = ctx.stream_rows_begin();
       done = tmm_dev(terms, K, sq, tmpN.p, tmpK.p, true, ~(u64)0, ready);
       if (done) ctx.stream_rows_copy(tmpN.p, a, N); /* after the launch: a pageable source blocks the host per chunk */
@@ -663,6 +663,15 @@ struct OuterBase {
     obd::launch_getmat(ctx, plan(pr, 0, -1), tmpP.p, ld);
     for (u64 k = 0; k < K; ++k) d2h(out + k * N, tmpP.p + k * ld, N);
   }
+  /* the explicit basis matrix (h < 0, getmat :649) or its derivative in hyper-parameter h (one slice of
+   * getmat_gradhyp :663, dogetmge_ linalg.cpp:741-750: the factor of dimension hypmatch[h] replaced by its gradient
+   * column) in HBM: ld x K, pad rows zero */
+  void getmat_dev(const u64* terms, u64 K, int h, double* out_dev) {
+    if (h >= 0 && !dograd) throw std::logic_error("outerbase was built without gradients");
+    if (N < ld) OB_CUDA(cudaMemsetAsync(out_dev, 0, ld * K * sizeof(double), ctx.stream));
+    obd::DevProgram* pr = program(terms, K, h < 0 ? -1 : (int)hypmatch[h]);
+    obd::launch_getmat(ctx, plan(pr, 0, h), out_dev, ld);
+  }
   void getbase(u64 dim1, double* out) {
     if (dim1 < 1 || dim1 > d) throw std::range_error("dim out of range");
     ensure_all();
@@ -679,7 +688,8 @@ struct Lpdf {
   std::vector<double> grad, gradhyp, gradpara, para, coeff, totdiaghess, para0, paravar;
   std::vector<u64> terms; /* K x d */
   u64 d = 0;
-  bool didfulltothess = false, didnotothess = true;
+  std::vector<double> tothess; /* K x K, fit.h:33 */
+  bool didfulltothess = false, didnotothess = true, fullhess = false;
   bool compute_val = true, compute_grad = true, compute_gradhyp = false, compute_gradpara = false;
   u64 npara = 0, nterms = 0, cg_iters = 0;
   virtual ~Lpdf() {}
@@ -708,12 +718,74 @@ struct Lpdf {
   virtual bool diaghessgradhyp_dot(const std::vector<double>&, std::vector<double>&) { return false; }
   virtual bool can_diaghessgradhyp_dot() const { return false; }
   virtual void settotdiaghess(const std::vector<double>& dh) { totdiaghess = dh; didfulltothess = false; didnotothess = false; }
+  /* full Hessian, fit.h:81-88: K x K, K x K x H, K x K x npara (column-major, slice after slice); empty when the
+   * object has none (loglik_gauss, loglik_gda) */
+  virtual void settothess(const std::vector<double>& h) { tothess = h; didfulltothess = true; didnotothess = false; }
+  virtual std::vector<double> hess() { return {}; }
+  virtual std::vector<double> hessgradhyp() { return {}; }
+  virtual std::vector<double> hessgradpara() { return {}; }
   virtual u64 nhyp() const { return 0; }
   virtual u64 nrow() const { return 0; }
+
+  /* dense K x K algebra of the full-Hessian branch: host side, like every other K-sized object of the lpdf family */
+  /* solve A X = B by elimination with partial pivoting (Armadillo solve(): LAPACK dgesv); B is n x m */
+  static std::vector<double> dense_solve(std::vector<double> A, std::vector<double> B, u64 n, u64 m) {
+    if (A.size() != n * n || B.size() != n * m) throw std::invalid_argument("solve(): incompatible dimensions");
+    for (u64 k = 0; k < n; ++k) {
+      u64 piv = k;
+      for (u64 i = k + 1; i < n; ++i) if (std::fabs(A[i + k * n]) > std::fabs(A[piv + k * n])) piv = i;
+      if (A[piv + k * n] == 0.0) throw std::runtime_error("solve(): solution not found");
+      if (piv != k) {
+        for (u64 j = 0; j < n; ++j) std::swap(A[k + j * n], A[piv + j * n]);
+        for (u64 j = 0; j < m; ++j) std::swap(B[k + j * n], B[piv + j * n]);
+      }
+      const double inv = 1.0 / A[k + k * n];
+      for (u64 i = k + 1; i < n; ++i) A[i + k * n] *= inv; /* multipliers */
+      for (u64 j = k + 1; j < n; ++j) {
+        const double akj = A[k + j * n];
+        if (akj == 0.0) continue;
+        for (u64 i = k + 1; i < n; ++i) A[i + j * n] -= A[i + k * n] * akj;
+      }
+      for (u64 j = 0; j < m; ++j) {
+        const double bkj = B[k + j * n];
+        if (bkj == 0.0) continue;
+        for (u64 i = k + 1; i < n; ++i) B[i + j * n] -= A[i + k * n] * bkj;
+      }
+    }
+    for (u64 j = 0; j < m; ++j)
+      for (u64 ii = n; ii-- > 0;) {
+        const double x = B[ii + j * n] / A[ii + ii * n];
+        B[ii + j * n] = x;
+        for (u64 i = 0; i < ii; ++i) B[i + j * n] -= A[i + ii * n] * x;
+      }
+    return B;
+  }
+  static std::vector<double> dense_inv(const std::vector<double>& A, u64 n) {
+    std::vector<double> I(n * n, 0.0);
+    for (u64 i = 0; i < n; ++i) I[i + i * n] = 1.0;
+    return dense_solve(A, std::move(I), n, n);
+  }
+
+  /* lpdf::optnewton, fit.cpp:98-131: one Newton step on the full Hessian */
+  virtual void optnewton() {
+    fullhess = true;
+    compute_val = true; compute_grad = true; compute_gradhyp = false; compute_gradpara = false;
+    if (coeff.size() != nterms) coeff.assign(nterms, 0.0);
+    update(std::vector<double>(coeff));
+    const std::vector<double> h = hess();
+    const std::vector<double> r = grad;
+    if (!all_finite(h) && !all_finite(r)) { val = -std::numeric_limits<double>::infinity(); return; }
+    const std::vector<double> step = dense_solve(h, r, nterms, 1); /* throws on an empty Hessian as the reference's solve() does */
+    for (u64 i = 0; i < nterms; ++i) coeff[i] += step[i];
+    compute_gradhyp = true; compute_gradpara = true;
+    update(std::vector<double>(coeff));
+    compute_gradhyp = false; compute_gradpara = false;
+  }
 
   /* lpdf::optcg, fit.cpp:37-96.  The K-length algebra runs on the host in the
    * reference's order (Armadillo's two-accumulator accu); update/hessmult are the GPU. */
   virtual void optcg(double tol, u64 maxepch) {
+    fullhess = false;
     compute_val = true; compute_grad = true; compute_gradhyp = false; compute_gradpara = false;
     if (coeff.size() != nterms) coeff.assign(nterms, 0.0);
     update(std::vector<double>(coeff));
@@ -839,6 +911,16 @@ struct LogprGauss : Lpdf { /* logpr_gauss.cpp:41-145 */
     for (u64 i = 0; i < nterms; ++i) { const double s = coeffsd[i] * sca; o[i] = -2. / (s * s); }
     return o;
   }
+  /* hess / hessgradhyp / hessgradpara, logpr_gauss.cpp:153-186: the diagonal forms on the diagonal of K x K slices */
+  static std::vector<double> on_diagonals(const std::vector<double>& dg, u64 K) {
+    const u64 S = K ? dg.size() / K : 0;
+    std::vector<double> o(K * K * S, 0.0);
+    for (u64 s = 0; s < S; ++s) for (u64 i = 0; i < K; ++i) o[i + i * K + s * K * K] = dg[i + s * K];
+    return o;
+  }
+  std::vector<double> hess() override { return on_diagonals(diaghess(), nterms); }
+  std::vector<double> hessgradhyp() override { return on_diagonals(diaghessgradhyp(), nterms); }
+  std::vector<double> hessgradpara() override { return on_diagonals(diaghessgradpara(), nterms); }
   u64 nhyp() const override { return om->nhyp(); }
 };
 
@@ -1062,6 +1144,52 @@ struct LoglikGauss : Lpdf { /* loglik_gauss.cpp:41-179 */
 /* loglik_gda (src/lpdfs/loglik_gda.cpp:47-239): the stage-1 likelihood of obfit, built on a <= 3*numb-row subsample
  * (R/fitting.R:79-84).  Every Phi-type product runs on the GPU kernels through the outerbase operators; the
  * N-vector bookkeeping around them (per-row noise scale and its derivatives) follows the reference on the host. */
+/* loglik_std, src/lpdfs/loglik_std.cpp:41-203: loglik_gauss's model (same value, gradients, Hessian products and
+ * diagonals -- the formulas of :100-165 are loglik_gauss.cpp:110-179's) plus the full K x K Hessian that lpdf::optnewton
+ * and the full branch of lpdfvec::buildhess need.  The reference keeps the explicit N x K basis and its N x K x H cube
+ * for everything; here only the Hessians touch explicit matrices, and they are contractions over the rows on the FP64
+ * tensor cores: hess = Phi^T . getmat (tprodmm_(mat) with K right-hand sides, phi_tm_spec), one more per
+ * hyper-parameter for hessgradhyp.  Rows sharded over ranks like loglik_gauss (the products sum over ranks). */
+struct LoglikStd : LoglikGauss {
+  DevBuf<double> basis, hbuf;
+  LoglikStd(Ctx& c, const OuterMod* om_, const u64* t, u64 K, const double* yh, const double* xh, u64 N_)
+      : LoglikGauss(c, om_, t, K, yh, xh, N_) {}
+  /* Phi^T . M for an explicit ld x K matrix M in `basis`; K x K on the host */
+  std::vector<double> gram(int h) {
+    const u64 K = nterms;
+    basis.ensure(ob.ld * std::max<u64>(K, 1));
+    hbuf.ensure(K * K + 1);
+    ob.getmat_dev(terms.data(), K, h, basis.p);
+    ob.tmm_mat_dev(terms.data(), K, 0, basis.p, ob.ld, K, hbuf.p);
+    std::vector<double> o(K * K);
+    ob.d2h(o.data(), hbuf.p, K * K);
+    return o;
+  }
+  std::vector<double> hess() override { /* :173-176 */
+    const u64 K = nterms;
+    std::vector<double> g = gram(-1), o(K * K);
+    const double c = std::exp(-2 * para[0]);
+    /* Phi^T Phi is symmetric; the kernel's (i, j) and (j, i) differ in the last bit (one side is recomputed) */
+    for (u64 j = 0; j < K; ++j) for (u64 i = 0; i < K; ++i) o[i + j * K] = c * (0.5 * (g[i + j * K] + g[j + i * K]));
+    return o;
+  }
+  std::vector<double> hessgradhyp() override { /* :183-195 */
+    const u64 K = nterms, H = ob.H;
+    std::vector<double> o(K * K * H);
+    const double c = std::exp(-2 * para[0]);
+    for (u64 h = 0; h < H; ++h) {
+      const std::vector<double> g = gram((int)h);
+      for (u64 j = 0; j < K; ++j) for (u64 i = 0; i < K; ++i) o[i + j * K + h * K * K] = c * g[i + j * K] + c * g[j + i * K];
+    }
+    return o;
+  }
+  std::vector<double> hessgradpara() override { /* :202-206 */
+    std::vector<double> o = hess();
+    for (double& v : o) v = -2 * v;
+    return o;
+  }
+};
+
 struct LoglikGda : Lpdf {
   Ctx& ctx;
   const OuterMod* om;
@@ -1205,6 +1333,7 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
   std::vector<double> gradhyp_margadj, gradpara_margadj;
   bool domargadj = true;
   std::vector<double> diaghessv, diaghessgradhypv, diaghessgradparav;
+  std::vector<double> hessv, hessgradhypv, hessgradparav; /* full-Hessian branch, fit.h:121-123 */
   bool hyp_matrix_stale = false; /* buildhess took the contracted route: the K x H matrix is formed on demand */
   bool redohess = true;
   Lpdf* kid[2];
@@ -1255,7 +1384,102 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
     return out;
   }
   void settotdiaghess(const std::vector<double>& dh) override { totdiaghess = dh; for (Lpdf* l : kid) l->settotdiaghess(dh); }
-  void buildhess() { /* fit.cpp:252-267 */
+  void settothess(const std::vector<double>& h) override { tothess = h; for (Lpdf* l : kid) l->settothess(h); } /* :609-612 */
+  std::vector<double> hess() override { return hessv; }
+  std::vector<double> hessgradhyp() override { return hessgradhypv; }
+  std::vector<double> hessgradpara() override { return hessgradparav; }
+  static std::vector<double> sum_same_size(std::vector<double> a, const std::vector<double>& b, const char* what) {
+    if (a.size() != b.size()) throw std::invalid_argument(std::string("addition: incompatible dimensions (") + what + ")");
+    for (u64 i = 0; i < a.size(); ++i) a[i] += b[i];
+    return a;
+  }
+  std::vector<double> hessgradpara_() { /* :539-549 */
+    const u64 K = nterms, KK = K * K;
+    std::vector<double> out(KK * para.size(), 0.0);
+    for (int c = 0; c < 2; ++c) {
+      const std::vector<double> h = kid[c]->hessgradpara();
+      const u64 nc = paraend[c] + 1 - parasrt[c];
+      if (h.size() != KK * nc) throw std::invalid_argument("copy into subcube: incompatible dimensions");
+      std::copy(h.begin(), h.end(), out.begin() + parasrt[c] * KK);
+    }
+    return out;
+  }
+  /* the full branch of buildhess, fit.cpp:269-299.  log det and the inverse come from a Cholesky factor when the total
+   * Hessian is positive definite (it is at every point optnewton reaches), else from the symmetric eigen-decomposition
+   * the reference uses for both */
+  void buildhess_full() {
+    const u64 K = nterms, KK = K * K;
+    hessv = sum_same_size(kid[0]->hess(), kid[1]->hess(), "hess");
+    settothess(hessv);
+    if (!domargadj) return;
+    hessgradhypv = sum_same_size(kid[0]->hessgradhyp(), kid[1]->hessgradhyp(), "hessgradhyp");
+    hessgradparav = hessgradpara_();
+    if (hessv.size() != KK) throw std::invalid_argument("eig_sym(): given matrix must be square sized");
+    std::vector<double> L = hessv, hessi;
+    bool pd = true;
+    for (u64 j = 0; j < K && pd; ++j) { /* column Cholesky, lower triangle in place */
+      double djj = L[j + j * K];
+      for (u64 p = 0; p < j; ++p) djj -= L[j + p * K] * L[j + p * K];
+      if (!(djj > 0.0)) { pd = false; break; }
+      djj = std::sqrt(djj);
+      L[j + j * K] = djj;
+      for (u64 i = j + 1; i < K; ++i) {
+        double v = L[i + j * K];
+        for (u64 p = 0; p < j; ++p) v -= L[i + p * K] * L[j + p * K];
+        L[i + j * K] = v / djj;
+      }
+    }
+    if (pd) {
+      std::vector<double> t(K);
+      for (u64 i = 0; i < K; ++i) t[i] = 2.0 * std::log(L[i + i * K]);
+      val_margadj = -0.5 * obh::sum2(t.data(), K);
+      /* inverse = L^-T L^-1: invert the triangle column by column, then multiply */
+      std::vector<double> Li(KK, 0.0);
+      for (u64 j = 0; j < K; ++j) {
+        Li[j + j * K] = 1.0 / L[j + j * K];
+        for (u64 i = j + 1; i < K; ++i) {
+          double v = 0.0;
+          for (u64 p = j; p < i; ++p) v -= L[i + p * K] * Li[p + j * K];
+          Li[i + j * K] = v / L[i + i * K];
+        }
+      }
+      hessi.assign(KK, 0.0);
+      for (u64 j = 0; j < K; ++j)
+        for (u64 i = j; i < K; ++i) {
+          double v = 0.0;
+          for (u64 p = i; p < K; ++p) v += Li[p + i * K] * Li[p + j * K];
+          hessi[i + j * K] = v; hessi[j + i * K] = v;
+        }
+    } else {
+      obh::Mat S(K, K), V;
+      S.a = hessv;
+      std::vector<double> w;
+      obh::sym_eig_desc(S, w, V);
+      std::vector<double> t(K);
+      for (u64 i = 0; i < K; ++i) t[i] = std::log(w[i]);
+      val_margadj = -0.5 * obh::sum2(t.data(), K);
+      hessi.assign(KK, 0.0);
+      for (u64 j = 0; j < K; ++j)
+        for (u64 i = 0; i < K; ++i) {
+          double v = 0.0;
+          for (u64 p = 0; p < K; ++p) v += V(i, p) * V(j, p) / w[p];
+          hessi[i + j * K] = v;
+        }
+    }
+    std::vector<double> tm(KK);
+    const u64 H = KK ? hessgradhypv.size() / KK : 0, P = para.size();
+    gradhyp_margadj.assign(H, 0.0);
+    for (u64 l = 0; l < H; ++l) {
+      for (u64 i = 0; i < KK; ++i) tm[i] = hessgradhypv[i + l * KK] * hessi[i];
+      gradhyp_margadj[l] = -0.5 * obh::sum2(tm.data(), KK);
+    }
+    gradpara_margadj.assign(P, 0.0);
+    for (u64 l = 0; l < P; ++l) {
+      for (u64 i = 0; i < KK; ++i) tm[i] = hessgradparav[i + l * KK] * hessi[i];
+      gradpara_margadj[l] = -0.5 * obh::sum2(tm.data(), KK);
+    }
+  }
+  void buildhess() { /* fit.cpp:252-301 */
     if (redohess) {
       diaghessv = diaghess_();
       settotdiaghess(diaghessv);
@@ -1287,6 +1511,7 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
           gradpara_margadj[h] = -0.5 * obh::sum2(t.data(), K);
         }
       }
+      if (fullhess) buildhess_full();
     }
     redohess = false;
   }
@@ -1376,6 +1601,7 @@ struct LpdfVec : Lpdf { /* fit.cpp:174-267,310-428,557-607 */
     return true;
   }
   void optcg(double tol, u64 maxepch) override {
+    fullhess = false; /* fit.cpp:38 */
     if (!optcg_device(tol, maxepch)) Lpdf::optcg(tol, maxepch);
   }
   std::vector<double> diaghess() override { return diaghessv; }
@@ -1422,6 +1648,38 @@ struct PredGauss { /* loglik_gauss.cpp:196-227 */
     ob->mm(1, terms.data(), K, coeffvar.data(), out);
     const double c = std::exp(2 * para[0]);
     for (u64 i = 0; i < ob->N; ++i) out[i] += c;
+  }
+};
+
+struct PredrStd { /* loglik_std.cpp:219-257 */
+  Ctx& ctx;
+  const OuterMod* om;
+  std::vector<double> para, coeff, coeffcov; /* K x K */
+  std::vector<u64> terms;
+  u64 K, d;
+  std::unique_ptr<OuterBase> ob;
+  DevBuf<double> cov_dev, prod, basis, outv;
+  PredrStd(LoglikStd& lk) : ctx(lk.ctx), om(lk.om), para(lk.para), coeff(lk.coeff), terms(lk.terms), K(lk.nterms), d(lk.d) {
+    ob.reset(new OuterBase(ctx, om, lk.x_host.data(), lk.N, false, terms.data(), K));
+    if (coeff.size() != K) coeff.assign(K, 0.0);
+    coeffcov.assign(K * K, 0.0);
+    if (!lk.didnotothess) {
+      if (lk.didfulltothess) coeffcov = Lpdf::dense_inv(lk.tothess, K);
+      /* as written in the reference (:229): the diagonal of the total Hessian itself, not its inverse */
+      else for (u64 i = 0; i < K; ++i) coeffcov[i + i * K] = lk.totdiaghess[i];
+    }
+  }
+  void update(const double* x, u64 N) { ob.reset(new OuterBase(ctx, om, x, N, false, terms.data(), K)); }
+  void mean(double* out) { ob->mm(0, terms.data(), K, coeff.data(), out); }
+  void var(double* out) { /* rowsum((Phi coeffcov) % Phi) + exp(2 para) */
+    const u64 N = ob->N, ld = ob->ld;
+    if (N == 0) return;
+    cov_dev.upload(coeffcov, ctx.stream);
+    prod.ensure(ld * std::max<u64>(K, 1)); basis.ensure(ld * std::max<u64>(K, 1)); outv.ensure(ld);
+    ob->mm_mat_dev(terms.data(), K, 0, cov_dev.p, K, prod.p, ld);
+    ob->getmat_dev(terms.data(), K, -1, basis.p);
+    obd::launch_rowdot(ctx, prod.p, basis.p, N, K, ld, std::exp(2 * para[0]), outv.p);
+    ob->d2h(out, outv.p, N);
   }
 };
 

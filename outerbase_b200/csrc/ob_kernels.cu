@@ -899,6 +899,7 @@ Ctx::Ctx(int dev) : device(dev) {
   OB_CUDA(cudaMallocHost(&pinned, 4096 * sizeof(double)));
   if (const char* e = getenv("OB_DSWEEP")) dsweep = std::string(e) != "0";
   if (const char* e = getenv("OB_DEVICE_CG")) device_cg = std::string(e) != "0";
+  if (const char* e = getenv("OB_OVERLAP")) overlap = std::string(e) != "0";
   if (const char* e = getenv("OB_SPEC")) { /* 0 | 1 | auto */
     const std::string v(e);
     spec_mode = v == "0" ? 0 : (v == "1" ? 1 : 2);
@@ -1432,12 +1433,27 @@ __global__ void gather_coef_blocks_kernel(const double* __restrict__ A, unsigned
   const int s = idx >> 6, c = idx & 63;
   double v = 0.0;
   if (s < nslots && c < ncols) { const int t = slot_term[s]; if (t >= 0) v = A[(unsigned long long)t + (col0 + c) * K]; }
-  out[(size_t)s * 64 + (c ^ ((s & 1) << 3))] = v;
+  out[(size_t)s * 64 + (c ^ ((s & 3) << 2))] = v; /* phi_am_spec's bank swizzle */
 }
 void launch_gather_coef_blocks(Ctx& c, const double* A, u64 K, u64 col0, int ncols, const int32_t* slot_term, int nslots, int nrows, double* out) {
   const int n = nrows * 64;
   gather_coef_blocks_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(A, K, col0, ncols, slot_term, nslots, nrows, out);
   check_launch(c, "gather_coef_blocks_kernel");
+}
+
+/* out[n] = add + sum_k A[n, k] * B[n, k], k ascending (predr_std::var, loglik_std.cpp:251-257: sum(adj % basismat, 1)) */
+__global__ void rowdot_kernel(const double* __restrict__ A, const double* __restrict__ B, unsigned long long N, unsigned long long K,
+                              unsigned long long ld, double add, double* __restrict__ out) {
+  const unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double s = 0.0;
+  for (unsigned long long k = 0; k < K; ++k) s += A[n + k * ld] * B[n + k * ld];
+  out[n] = s + add;
+}
+void launch_rowdot(Ctx& c, const double* A, const double* B, u64 N, u64 K, u64 ld, double add, double* out) {
+  if (N == 0) return;
+  rowdot_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(A, B, N, K, ld, add, out);
+  check_launch(c, "rowdot_kernel");
 }
 
 void launch_fill(Ctx& c, double* p, u64 n, double v) {

@@ -439,7 +439,7 @@ bool launch_phi_am_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const double*
   p.off_flags = 128;
   q.off_coef = 128 + 256;
   q.off_phi = q.off_coef + 2 * KC * 64 * 8;
-  p.off_tile = q.off_phi + MW * KC * 40 * 8;
+  p.off_tile = q.off_phi + MW * KC * 36 * 8; /* OBS_PHI_STRIDE */
   p.tile_doubles = (unsigned)((p.ncol + 1) * TR);
   p.nstage = 1;
   const size_t smem = p.off_tile + (size_t)p.tile_doubles * 8;

@@ -151,8 +151,9 @@ def lpdfwrapper(parlist, om, logpdf, newt=False, cgsteps=100, cgtol=0.001):
         logpdf.updateom()
         logpdf.updatepara(parlist["para"])
         if newt:
-            raise NotImplementedError("optnewton belongs to loglik_std (SURVEY 8f rank 4)")
-        logpdf.optcg(cgtol, cgsteps)
+            logpdf.optnewton()  # :218 -- needs a likelihood with a full Hessian (loglik_std)
+        else:
+            logpdf.optcg(cgtol, cgsteps)
         gval = dict(parlist)
         gval["hyp"] = -np.asarray(logpdf.gradhyp) - np.asarray(om.hyplpdf_grad(parlist["hyp"]))
         gval["para"] = -np.asarray(logpdf.gradpara) - np.asarray(logpdf.paralpdf_grad(parlist["para"]))

@@ -382,3 +382,72 @@ def test_pruned_basis_layout_grows_with_the_terms(gpu, oracle):
         assert abs(a[0] - b[0]) <= 1e-8 * abs(b[0])
         assert relerr(a[1], b[1]) < 1e-8 and relerr(a[2], b[2]) < 1e-7
     assert relerr(res["g"][1][3], res["o"][1][3]) < 1e-8 and relerr(res["g"][1][4], res["o"][1][4]) < 1e-7
+
+
+@pytest.mark.parametrize("spec_mode", [1, 2])
+@pytest.mark.parametrize("N,K", [(200, 60), (600, 150), (20000, 100)])
+def test_loglik_std_optnewton_parity(gpu, oracle, N, K, spec_mode):
+    """loglik_std (src/lpdfs/loglik_std.cpp:41-257), the full-Hessian branch of lpdfvec (fit.cpp:269-299) and
+    lpdf::optnewton (fit.cpp:98-131) against the oracle (pinned to the unmodified reference at these shapes by
+    tests/test_oracle_ref.py): hess = Phi^T Phi and its hyper-gradient slices come from the tensor-core Phi^T . A kernel
+    (spec 1) or the column loop (spec 2, a cold table).  1e-8 like every other fit quantity; N = 20000 is a row-chunked
+    basis, where the reference itself cannot run loglik_std (getmge_, linalg.cpp:788-810) and the oracle applies the
+    unchunked formula."""
+    knots = [np.arange(0.001, 0.999, 0.05)] * 8
+    gpu.set_option("spec", spec_mode)
+    try:
+        out = {}
+        for name, lib in (("o", oracle), ("g", gpu)):
+            om, x, y, terms, rng = make_problem(lib, N, K, covs=["mat25"] * 8, knots=knots)
+            lk, pr = lib.loglik_std(om, terms, y, x), lib.logpr_gauss(om, terms)
+            c, g = rng.normal(size=K) / 50, rng.normal(size=K)
+            for l in (lk, pr):
+                l.compute_gradhyp = True; l.compute_gradpara = True
+            lk.updatepara([np.log(0.2)])
+            lk.update(c); pr.update(c)
+            res = dict(val=lk.val, grad=np.array(lk.grad), gradhyp=np.array(lk.gradhyp), gradpara=np.array(lk.gradpara), yhat=np.array(lk.yhat),
+                       hm=lk.hessmult(g), dh=lk.diaghess(), dhh=lk.diaghessgradhyp(), dhp=lk.diaghessgradpara(),
+                       hess=lk.hess(), hgh=lk.hessgradhyp(), hgp=lk.hessgradpara(),
+                       pr_hess=pr.hess(), pr_hgh=pr.hessgradhyp(), pr_hgp=pr.hessgradpara())
+            vec = lib.lpdfvec(lk, pr)
+            for domarg in (True, False):
+                vec.domarg = domarg
+                vec.updatepara(np.array(vec.para) + 0.05)
+                vec.set_coeff(np.zeros(K))
+                vec.optnewton()
+                res.update({f"v{domarg}_val": vec.val, f"v{domarg}_coeff": np.array(vec.coeff), f"v{domarg}_grad": np.array(vec.grad),
+                            f"v{domarg}_gradhyp": np.array(vec.gradhyp), f"v{domarg}_gradpara": np.array(vec.gradpara),
+                            f"v{domarg}_tothess": vec.tothess})
+            pd = lib.predictor(lk)
+            xn = np.asfortranarray(np.random.default_rng(5).uniform(size=(77, 8)))
+            pd.update(xn)
+            res.update(pm=pd.mean(), pv=pd.var())
+            lg = lib.loglik_gauss(om, terms, y, x)
+            assert lg.hess().size == 0 and lg.hessgradhyp().size == 0
+            with pytest.raises((ValueError, RuntimeError)):  # vignettes/speed.Rmd:74-76: optnewton on loglik_gauss throws
+                lib.lpdfvec(lg, lib.logpr_gauss(om, terms)).optnewton()
+            out[name] = res
+        for k, v in out["o"].items():
+            if k.endswith("_grad"):  # the gradient at the optimum is rounding noise: absolute, on the scale of the first gradient
+                assert np.abs(v - out["g"][k]).max() < 1e-7 * np.abs(out["o"]["grad"]).max(), k
+            else:
+                assert relerr(v, out["g"][k]) < 1e-8, k
+        assert np.array_equal(out["g"]["hess"], out["g"]["hess"].T)
+    finally:
+        gpu.set_option("spec", 2)
+
+
+def test_bfgs_lpdf_with_newton_steps(gpu, oracle):
+    """BFGS_lpdf(om, logpdf, newt = TRUE) -- R/outersupport.R:195-226 with lpdf$optnewton for the coefficients
+    (vignettes/learning.Rmd:146-160) -- GPU against the oracle."""
+    from outerbase_b200 import fitting
+    knots = [np.arange(0.001, 0.999, 0.05)] * 8
+    res = {}
+    for name, lib in (("o", oracle), ("g", gpu)):
+        om, x, y, terms, rng = make_problem(lib, 300, 40, covs=["mat25"] * 8, knots=knots)
+        vec = lib.lpdfvec(lib.loglik_std(om, terms, y, x), lib.logpr_gauss(om, terms))
+        r = fitting.BFGS_lpdf(om, vec, newt=True)
+        res[name] = (r["optid"]["val"], np.asarray(r["parlist"]["hyp"]), np.asarray(r["parlist"]["para"]), np.array(vec.coeff))
+    assert abs(res["g"][0] - res["o"][0]) < 1e-6 * abs(res["o"][0])
+    for i in (1, 2, 3):
+        assert relerr(res["g"][i], res["o"][i]) < 1e-4, i

@@ -268,6 +268,78 @@ def test_loglik_gda_bitwise(oracle, reference, N, K):
         np.testing.assert_array_equal(v, out["r"][k], err_msg=k)
 
 
+@pytest.mark.parametrize("N,K", [(200, 60), (600, 150)])
+def test_loglik_std_optnewton_full_hessian(oracle, reference, N, K):
+    """loglik_std + predr_std (src/lpdfs/loglik_std.cpp:41-257), logpr_gauss::hess* (logpr_gauss.cpp:153-186), the
+    full-Hessian branch of lpdfvec::buildhess (fit.cpp:269-299) and lpdf::optnewton (fit.cpp:98-131), as
+    vignettes/learning.Rmd:92-160 uses them.  loglik_std has no setnthreads, so its basis is built with every core and
+    the reference's short-basis race on basescale (modandbase.cpp:600-607) leaves rounding-level differences: 1e-12.
+    N <= 600 keeps the basis unchunked -- getmge_'s chunked branch cannot work (linalg.cpp:788-810)."""
+    knots = [np.arange(0.001, 0.999, 0.05)] * 8
+    out = {}
+    for name, lib in (("o", oracle), ("r", reference)):
+        om, x, y, terms, rng = make_problem(lib, N, K, covs=["mat25"] * 8, knots=knots)
+        lk, pr = lib.loglik_std(om, terms, y, x), lib.logpr_gauss(om, terms)
+        c, g = rng.normal(size=K) / 50, rng.normal(size=K)
+        for l in (lk, pr):
+            l.compute_gradhyp = True; l.compute_gradpara = True
+        lk.updatepara([np.log(0.2)])
+        lk.update(c); pr.update(c)
+        res = dict(val=lk.val, grad=np.array(lk.grad), gradhyp=np.array(lk.gradhyp), gradpara=np.array(lk.gradpara), yhat=np.array(lk.yhat),
+                   hm=lk.hessmult(g), dh=lk.diaghess(), dhh=lk.diaghessgradhyp(), dhp=lk.diaghessgradpara(),
+                   hess=lk.hess(), hgh=lk.hessgradhyp(), hgp=lk.hessgradpara(),
+                   pr_hess=pr.hess(), pr_hgh=pr.hessgradhyp(), pr_hgp=pr.hessgradpara())
+        assert res["hess"].shape == (K, K) and res["hgh"].shape == (K, K, lk._sizes()[2]) and res["hgp"].shape == (K, K, 1)
+        vec = lib.lpdfvec(lk, pr)
+        for domarg in (True, False):
+            vec.domarg = domarg
+            vec.updatepara(np.array(vec.para) + 0.05)
+            vec.set_coeff(np.zeros(K))
+            vec.optnewton()
+            res.update({f"v{domarg}_val": vec.val, f"v{domarg}_coeff": np.array(vec.coeff), f"v{domarg}_grad": np.array(vec.grad),
+                        f"v{domarg}_gradhyp": np.array(vec.gradhyp), f"v{domarg}_gradpara": np.array(vec.gradpara),
+                        f"v{domarg}_tothess": vec.tothess, f"v{domarg}_hess": vec.hess()})
+        # a Newton step on a quadratic lands on the optimum: the gradient vanishes
+        assert np.abs(vec.grad).max() < 1e-6 * np.abs(res["grad"]).max()
+        pd = lib.predictor(lk)
+        res.update(pm0=pd.mean(), pv0=pd.var())
+        xn = np.asfortranarray(np.random.default_rng(5).uniform(size=(77, 8)))
+        pd.update(xn)
+        res.update(pm=pd.mean(), pv=pd.var())
+        # objects without a full Hessian return empty matrices (fit.h:86-88)
+        lg = lib.loglik_gauss(om, terms, y, x)
+        assert lg.hess().size == 0 and lg.hessgradhyp().size == 0
+        out[name] = res
+    for k, v in out["o"].items():
+        if k.endswith("_grad"):  # the gradient AT the optimum is rounding noise: absolute, on the scale of the first gradient
+            assert np.abs(v - out["r"][k]).max() < 1e-10 * np.abs(out["o"]["grad"]).max(), k
+        else:
+            assert relerr(v, out["r"][k]) < 1e-12, k
+
+
+@pytest.mark.parametrize("N,K", [(200, 60), (600, 150)])
+def test_loglik_std_matches_loglik_gauss(oracle, N, K):
+    """The two likelihoods are the same model (vignettes/speed.Rmd:66): values, gradients and the diagonal of the Hessian
+    of loglik_std agree with loglik_gauss's, and diag(hess) is diaghess."""
+    knots = [np.arange(0.001, 0.999, 0.05)] * 8
+    om, x, y, terms, rng = make_problem(oracle, N, K, covs=["mat25"] * 8, knots=knots)
+    ls, lg = oracle.loglik_std(om, terms, y, x), oracle.loglik_gauss(om, terms, y, x)
+    c = rng.normal(size=K) / 50
+    for l in (ls, lg):
+        l.compute_gradhyp = True; l.compute_gradpara = True
+        l.updatepara([np.log(0.3)])
+        l.update(c)
+    assert abs(ls.val - lg.val) < 1e-12 * abs(lg.val)
+    for f in ("grad", "gradhyp", "gradpara", "yhat"):
+        assert relerr(getattr(ls, f), getattr(lg, f)) < 1e-12, f
+    assert relerr(ls.diaghess(), lg.diaghess()) < 1e-13 and relerr(ls.diaghessgradhyp(), lg.diaghessgradhyp()) < 1e-12
+    assert relerr(np.diag(ls.hess()), ls.diaghess()) < 1e-14
+    hgh = ls.hessgradhyp()
+    assert relerr(np.stack([np.diag(hgh[:, :, h]) for h in range(hgh.shape[2])], axis=1), ls.diaghessgradhyp()) < 1e-12
+    g = rng.normal(size=K)
+    assert relerr(ls.hess() @ g, ls.hessmult(g)) < 1e-12
+
+
 def test_blas_flavour_sensitivity(oracle, reference, reference_noblas):
     """What the unpinned BLAS under Armadillo is worth.  On SHARED basis matrices the linalg.h kernels do not depend on
     it beyond rounding; the basis build does (rotmat columns are divided by eigenvalues decaying like j^-6: SURVEY 7)."""

@@ -13,8 +13,8 @@ import sys
 import tempfile
 from pathlib import Path
 
-LENGTHS = [128, 160, 192, 256, 320]
-PADS = [0, 2048]      # DFMAs of never-executed code between two bodies: moves the bodies apart in the address space
+LENGTHS = [96, 192, 384, 768, 1536]
+PADS = [0]      # DFMAs of never-executed code between two bodies: moves the bodies apart in the address space
 COPIES = 12
 
 
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(384, 1) k_{L}_{PAD}(double* out, const double*
     k_{L}_{PAD}<<<148, nw * 32>>>(out, in, iters, distinct, cyc);
     cudaDeviceSynchronize();
     long long c = 0; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("body %5d DFMA (%6d B) + %6d B apart  warps/SM %2d  %s  %.3f DFMA/clk/SM\\n", {L}, {L} * 16, {PAD} * 16, nw, distinct ? "one body per warp " : "all warps one body", (double)nw * {L} * iters / (double)c);
+    printf("body %5d DFMA (%6d B)  warps/SM %2d  %s  %.3f DFMA/clk/SM\\n", {L}, {L} * 16, nw, distinct ? "one body per warp " : "all warps one body", (double)nw * {L} * iters / (double)c);
   }}""" for L in LENGTHS for PAD in PADS)
     s.append(f"""
 int main() {{

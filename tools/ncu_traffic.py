@@ -24,6 +24,8 @@ for r in rows[2:]:
     e["duration_us"] += val("gpu__time_duration.sum", False) * {"us": 1, "ms": 1e3, "ns": 1e-3, "msecond": 1e3, "usecond": 1, "nsecond": 1e-3}.get(u["gpu__time_duration.sum"], 1)
     for m, key in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
                    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex_pct"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+                   ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "dmma_pipe_pct"),
+                   ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared_wavefronts"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared_bank_conflicts"),
                    ("launch__registers_per_thread", "registers"), ("launch__block_size", "block"), ("launch__grid_size", "grid")):
         if m in d:
             e[key] = float(d[m].replace(",", ""))

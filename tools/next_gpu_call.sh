@@ -1,16 +1,25 @@
 #!/bin/bash
-# First GPU call of the next round (one B200): validates what round 1 built after its GPU budget ran out.
-#   gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh'
-# Everything lands in gpurun_out/next_*.  Each step has its own timeout: phi_d_spec has never run on a GPU.
+# Measurement pass of a round on ONE B200 (what profiles/r02_* were made with):
+#   gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh r02'
+# Everything lands in gpurun_out/<tag>_*.  Every step has its own timeout; nothing timed under ncu is a bench value.
 set -u
-mkdir -p gpurun_out
-# 1. the whole GPU suite as the driver runs it (buildhess / allreduce_dev changes included)
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/next_pytest.log
-# 2. the hyper-gradient sweep: parity against the per-hyper path and the oracle
-OB_TEST_DSWEEP=1 timeout 300 python -m pytest tests/test_gpu_spec.py -k hyper_gradient_sweep -x -q > gpurun_out/next_dsweep_test.log 2>&1; echo "dsweep test rc=$?"; tail -5 gpurun_out/next_dsweep_test.log
-# 3. what it buys: one BFGS objective evaluation with and without it
-timeout 300 python tools/dsweep_bench.py --config c3 > gpurun_out/next_dsweep_c3.json 2> gpurun_out/next_dsweep_c3.err; echo "dsweep c3 rc=$?"; cat gpurun_out/next_dsweep_c3.json
-timeout 600 python tools/dsweep_bench.py --config c4share > gpurun_out/next_dsweep_c4.json 2> gpurun_out/next_dsweep_c4.err; echo "dsweep c4 rc=$?"; cat gpurun_out/next_dsweep_c4.json
-# 4. ncu of the new kernel (only after the runs above exited 0)
-OB_DSWEEP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:phi_d_spec -c 2 -o gpurun_out/next_phi_d \
-  python tools/dsweep_bench.py --config c3 > gpurun_out/next_ncu.log 2>&1; echo "ncu rc=$?"
+T=${1:-r02}
+O=gpurun_out
+mkdir -p $O
+# 1. the whole GPU suite as the driver runs it
+timeout 900 python -m pytest tests -m gpu -x -q > $O/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/${T}_pytest_gpu.log
+# 2. the contract line (C3) and the other configs
+timeout 600 python bench.py > $O/${T}_bench_1gpu.json 2> $O/${T}_bench_1gpu.err; echo "bench rc=$?"; cat $O/${T}_bench_1gpu.json
+for c in c2 c4share c5 build; do
+  timeout 600 python bench.py --config $c > $O/${T}_bench_$c.json 2> $O/${T}_bench_$c.err; echo "bench $c rc=$?"; cat $O/${T}_bench_$c.json
+done
+# 3. launch list of the bench command (share of each kernel in the step).  OB_OVERLAP=0: ncu serialises kernels and copies,
+#    so the streamed-input kernel of the e2e leg would wait for rows that cannot arrive
+OB_OVERLAP=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${T}_launches.csv \
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/${T}_launches.log 2>&1; echo "launch list rc=$?"
+# 4. full captures: the two products of the step, then the multi-RHS tensor-core kernels of C5
+OB_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:phi_._spec -s 6 -c 2 -o $O/${T}_spec -f \
+  python bench.py --steps 2 --warmup 3 --no-optcg --no-cpu-baseline > $O/${T}_ncu_spec.log 2>&1; echo "ncu spec rc=$?"
+OB_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:phi_.m_spec -s 2 -c 2 -o $O/${T}_mat -f \
+  python bench.py --config c5 --steps 2 --warmup 2 --no-cpu-baseline > $O/${T}_ncu_mat.log 2>&1; echo "ncu mat rc=$?"
+ls -la $O | tail -20
