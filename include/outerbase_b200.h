@@ -211,6 +211,10 @@ int ob_spec_source_dot(const uint64_t* terms, uint64_t K, uint64_t d, char* buf,
  * src/linalg.cpp:583-637, on the FP64 tensor cores) for a table; info = {CTA types, most columns a type stages}. */
 int ob_spec_source_tmat(const uint64_t* terms, uint64_t K, uint64_t d, char* buf, uint64_t* len,
                         uint64_t* info /* 2 */);
+/* Test hook (no GPU needed): the source of the multi-right-hand-side kernel (phi_am_spec: prodmm_(mat),
+ * src/linalg.cpp:527-557, on the FP64 tensor cores) for a table; info = {coefficient blocks per pass, tile rows}. */
+int ob_spec_source_mat(const uint64_t* terms, uint64_t K, uint64_t d, char* buf, uint64_t* len,
+                       uint64_t* info /* 2 */);
 /* Test hook (no GPU needed): compile a source for sm_100a with NVRTC, bypassing the disk
  * cache; returns the cubin size. */
 int ob_spec_compile_check(const char* source, uint64_t* cubin_bytes, double* seconds);

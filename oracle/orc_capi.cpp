@@ -78,6 +78,7 @@ int orc_outerbase_specialize(orc_outerbase*, const uint64_t*, uint64_t, double* 
 int orc_outerbase_spec_state(orc_outerbase*, const uint64_t*, uint64_t, int* st) { if (st) *st = 0; return ORC_OK; }
 int orc_spec_source(const uint64_t*, uint64_t, uint64_t, const int*, char*, uint64_t*, uint64_t*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
 int orc_spec_source_dot(const uint64_t*, uint64_t, uint64_t, char*, uint64_t*, uint64_t*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
+int orc_spec_source_mat(const uint64_t*, uint64_t, uint64_t, char*, uint64_t*, uint64_t*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
 int orc_spec_source_tmat(const uint64_t*, uint64_t, uint64_t, char*, uint64_t*, uint64_t*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
 int orc_spec_compile_check(const char*, uint64_t*, double*) { g_err = "the oracle has no kernels"; return ORC_ERR_STATE; }
 

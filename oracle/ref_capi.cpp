@@ -122,6 +122,7 @@ int ref_outerbase_specialize(ref_outerbase*, const uint64_t*, uint64_t, double* 
 int ref_outerbase_spec_state(ref_outerbase*, const uint64_t*, uint64_t, int* st) { if (st) *st = 0; return REF_OK; }
 int ref_spec_source(const uint64_t*, uint64_t, uint64_t, const int*, char*, uint64_t*, uint64_t*) { g_err = "the reference has no kernels"; return REF_ERR_STATE; }
 int ref_spec_source_dot(const uint64_t*, uint64_t, uint64_t, char*, uint64_t*, uint64_t*) { g_err = "the reference has no kernels"; return REF_ERR_STATE; }
+int ref_spec_source_mat(const uint64_t*, uint64_t, uint64_t, char*, uint64_t*, uint64_t*) { g_err = "the reference has no kernels"; return REF_ERR_STATE; }
 int ref_spec_source_tmat(const uint64_t*, uint64_t, uint64_t, char*, uint64_t*, uint64_t*) { g_err = "the reference has no kernels"; return REF_ERR_STATE; }
 int ref_spec_compile_check(const char*, uint64_t*, double*) { g_err = "the reference has no kernels"; return REF_ERR_STATE; }
 int ref_debug_terms_eval(const uint64_t*, uint64_t, uint64_t, const uint64_t*, int, int, const double*, const double*, const double*, double,

@@ -110,6 +110,16 @@ class Library:
         self.call("spec_source_tmat", _p(t), _u(t.shape[0]), _u(t.shape[1]), buf, C.byref(n), info)
         return buf.value.decode(), {"types": info[0], "maxcols": info[1]}
 
+    def spec_source_mat(self, terms):
+        """Source of the multi-right-hand-side kernel (phi_am_spec) for a table; info = (blocks per pass, tile rows)."""
+        t = _terms(terms)
+        n = C.c_uint64(0)
+        info = (C.c_uint64 * 2)()
+        self.call("spec_source_mat", _p(t), _u(t.shape[0]), _u(t.shape[1]), None, C.byref(n), info)
+        buf = C.create_string_buffer(n.value)
+        self.call("spec_source_mat", _p(t), _u(t.shape[0]), _u(t.shape[1]), buf, C.byref(n), info)
+        return buf.value.decode(), tuple(int(v) for v in info)
+
     def spec_source_dot(self, terms):
         """CUDA source of the hyper-gradient sweep kernel (phi_d_spec) for a terms table (host only) -> (source, info)."""
         t = _terms(terms)

@@ -327,6 +327,20 @@ int ob_spec_source_tmat(const uint64_t* terms, uint64_t K, uint64_t d, char* buf
   *len = S.src.size() + 1;
   OB_CATCH
 }
+int ob_spec_source_mat(const uint64_t* terms, uint64_t K, uint64_t d, char* buf, uint64_t* len, uint64_t* info) {
+  OB_TRY
+  need(terms, "terms"); need(len, "len");
+  const obt::Program pa = obt::compile(terms, K, d, 1);
+  const obs::SpecSource S = obs::generate_mat(pa, obd::spec_default_options());
+  if (!S.ok) throw std::invalid_argument(S.why);
+  if (info) { info[0] = (u64)S.nacc; info[1] = (u64)S.tr_a; }
+  if (buf) {
+    if (*len < S.src.size() + 1) throw std::range_error("buffer too small");
+    std::memcpy(buf, S.src.c_str(), S.src.size() + 1);
+  }
+  *len = S.src.size() + 1;
+  OB_CATCH
+}
 int ob_spec_compile_check(const char* source, uint64_t* cubin_bytes, double* seconds) {
   OB_TRY
   need(source, "source");

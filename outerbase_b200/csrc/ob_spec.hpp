@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <stdexcept>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -321,9 +322,31 @@ inline int emit_mat(Emitter& e, const Program& P, int TR, int KC) {
   using namespace obt;
   int ia = 0;
   bool open = false;
-  auto begin_case = [&]() { if (!open) { e.f("case %d: {\n", ia / KC); open = true; } };
-  auto emitted = [&]() { if (++ia % KC == 0) { e.f("} break;\n"); open = false; } };
-  auto fac = [&](uint32_t col) { char b[64]; std::snprintf(b, sizeof b, "ldv(tp + %uu)", (unsigned)(col * TR) * 8u); return std::string(b); };
+  /* One case = the statements of KC emits.  Its basis-column loads are hoisted to the top of the case (each column
+   * once): the loads, the products and the parking stores are volatile asm statements that keep their order, and a
+   * load right in front of its use made every emit wait a full shared-memory latency (~40 cycles x KC per block, a
+   * quarter of the block's tensor-core time, profiles/r02_traffic.json c5: DMMA pipe 75 % active). */
+  Emitter loads, stmts;
+  std::map<uint32_t, int> have; /* column -> f index in this case */
+  auto begin_case = [&]() { if (!open) { loads.s.clear(); stmts.s.clear(); have.clear(); open = true; } };
+  auto end_case = [&]() {
+    e.f("case %d: {\n", (ia - 1) / KC);
+    e.s += loads.s;
+    e.s += stmts.s;
+    e.f("} break;\n");
+    open = false;
+  };
+  auto emitted = [&]() { if (++ia % KC == 0) end_case(); };
+  auto fac = [&](uint32_t col) {
+    auto it = have.find(col);
+    if (it == have.end()) {
+      it = have.emplace(col, (int)have.size()).first;
+      loads.f("const double f%d = ldv(tp + %uu);\n", it->second, (unsigned)(col * TR) * 8u);
+    }
+    char b[24];
+    std::snprintf(b, sizeof b, "f%d", it->second);
+    return std::string(b);
+  };
   e.f("double cu = 1.0, s0 = 1.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0, s8 = 0.0;\n");
   e.f("_Pragma(\"unroll 1\") for (int blk = 0; blk < OBS_NBLK; ++blk) {\nswitch (blk) {\n");
   for (uint32_t i = P.fwd_off[0];; ++i) {
@@ -332,23 +355,28 @@ inline int emit_mat(Emitter& e, const Program& P, int TR, int KC) {
     if (op == F_EMITZERO) continue;
     begin_case();
     if (op == F_LEAF) {
-      e.f("OBS_M_EMIT(%d, cu * %s);\n", ia % KC, fac(col).c_str());
+      stmts.f("OBS_M_EMIT(%d, cu * %s);\n", ia % KC, fac(col).c_str());
       emitted();
     } else if (op == F_DESC_CUR || op == F_DESC_STK) {
-      if (op == F_DESC_STK) e.f("cu = s%u * %s;\n", d - 1, fac(col).c_str());
-      else e.f("cu = cu * %s;\n", fac(col).c_str());
-      if (fl & FLAG_SAVE) e.f("s%u = cu;\n", d);
-      if (fl & FLAG_EMIT) { e.f("OBS_M_EMIT(%d, cu);\n", ia % KC); emitted(); }
+      if (op == F_DESC_STK) stmts.f("cu = s%u * %s;\n", d - 1, fac(col).c_str());
+      else stmts.f("cu = cu * %s;\n", fac(col).c_str());
+      if (fl & FLAG_SAVE) stmts.f("s%u = cu;\n", d);
+      if (fl & FLAG_EMIT) { stmts.f("OBS_M_EMIT(%d, cu);\n", ia % KC); emitted(); }
     } else if (op == F_ROOT) {
-      e.f("OBS_M_EMIT(%d, s0);\n", ia % KC);
+      stmts.f("OBS_M_EMIT(%d, s0);\n", ia % KC);
       emitted();
     } else if (op == F_LOADCUR) {
-      e.f("cu = s%u;\n", d);
+      stmts.f("cu = s%u;\n", d);
     }
   }
   const int n = ia;
-  if (ia % KC) { begin_case(); while (ia % KC) { e.f("OBS_M_EMIT(%d, 0.0);\n", ia % KC); ++ia; } e.f("} break;\n"); open = false; }
-  if (open) e.f("} break;\n");
+  if (ia % KC) { begin_case(); while (ia % KC) { stmts.f("OBS_M_EMIT(%d, 0.0);\n", ia % KC); ++ia; } end_case(); }
+  if (open) { /* trailing statements without an emit (cannot follow the last term of a well-formed program) */
+    e.f("case %d: {\n", ia / KC);
+    e.s += loads.s; e.s += stmts.s;
+    e.f("} break;\n");
+    open = false;
+  }
   e.f("default: break;\n}\nOBS_M_BLOCK()\n}\n");
   return n;
 }

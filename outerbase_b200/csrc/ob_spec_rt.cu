@@ -278,13 +278,15 @@ static void spec_launch(Ctx& c, cudaKernel_t kern, size_t& smem_set, int grid, i
 
 /* shared-memory layout: 16 mbarriers | coefficient copy (Phi a) | nstage tiles of (ncol + extra) columns */
 struct SpecGeom { int nstage = 0; unsigned off_vec = 0, off_tile = 0, tile_doubles = 0; size_t smem = 0; };
-/* `group` = consumer groups that take the tiles round-robin.  The stage count is a multiple of it, so that every
- * round of one stage goes to the SAME group: a group that met a stage of another group's could test its full
- * barrier two phases late, and an mbarrier parity wait cannot tell phase r from phase r + 2 (seen as wrong rows /
- * a launch failure once in a few runs with 4 groups on 5 or 6 stages). */
+/* `group` = consumer groups that take the tiles round-robin in a kernel WITHOUT the rounds[] guard (phi_d_spec): the
+ * stage count is then a multiple of it, so that every round of one stage goes to the SAME group -- a group that met a
+ * stage of another group's could test its full barrier two phases late, and an mbarrier parity wait cannot tell phase
+ * r from phase r + 2 (seen as wrong rows / a launch failure once in a few runs with 4 groups on 5 or 6 stages).
+ * phi_a_spec keeps a per-stage count of completed rounds in shared memory instead (ob_spec_scaffold.inc) and takes
+ * any stage count. */
 static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t vec_bytes, int want_stages, int group = 1) {
   SpecGeom g;
-  g.off_vec = 128 + 256; /* 16 mbarriers | 256 square flags | ... */
+  g.off_vec = 128 + 256 + 128; /* 16 mbarriers | 256 square flags | completed rounds per stage | ... */
   g.off_tile = (unsigned)(g.off_vec + vec_bytes);
   g.tile_doubles = (unsigned)((ncol + nextra) * TR);
   const size_t tile_bytes = (size_t)g.tile_doubles * 8;
@@ -298,9 +300,16 @@ static SpecGeom spec_geometry(const Ctx& c, int ncol, int nextra, int TR, size_t
 /* shrink the tile geometry until a table with `ncol` columns and `nslots` coefficient slots fits the
  * shared memory of the SM: fewer tiles in work first, then fewer rows per tile */
 obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, size_t nslots) {
+  /* Phi a: four 64-row tiles in work (2 warps each) want a fifth stage to load ahead; a table whose tiles leave room
+   * for four only (C4: 81 columns, 4000 coefficients) runs 10 % faster on two 128-row tiles of 4 warps
+   * (profiles/r02_spec_sweeps.txt) */
+  if (o.ra == 1 && o.qa == 2 && o.tga == 4 && !getenv("OB_SPEC_OPTS")) {
+    const size_t vec = std::max<size_t>(((nslots * 8 + 127) / 128) * 128, 8 * 32 * (size_t)(o.qa * o.tga + o.np));
+    if (spec_geometry(c, ncol, 1, 64, vec, 8).nstage < 5 && spec_geometry(c, ncol, 1, 128, vec, 8).nstage >= 2) { o.qa = 4; o.tga = 2; }
+  }
   for (;;) {
     const size_t vec = std::max<size_t>(((nslots * 8 + 127) / 128) * 128, 8 * 32 * (size_t)(o.qa * o.tga + o.np));
-    if (spec_geometry(c, ncol, 1, 32 * o.ra * o.qa, vec, 8, o.tga).nstage >= o.tga) break;
+    if (spec_geometry(c, ncol, 1, 32 * o.ra * o.qa, vec, 8).nstage >= o.tga) break;
     if (o.tga > 1) --o.tga;
     else if (o.qa > 1) o.qa /= 2;
     else if (o.ra > 1) o.ra /= 2;
@@ -312,7 +321,7 @@ obs::SpecOptions spec_adapt_options(const Ctx& c, obs::SpecOptions o, int ncol, 
 
 bool spec_fits(const Ctx& c, const SpecKernels& k, int ncol) {
   if (ncol + 2 > 256) return false; /* one square flag per tile column in a 256-byte block */
-  return spec_geometry(c, ncol, 1, k.tr_a, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (k.opt.qa * k.opt.tga + k.opt.np)), 8, k.opt.tga).nstage >= k.opt.tga &&
+  return spec_geometry(c, ncol, 1, k.tr_a, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (k.opt.qa * k.opt.tga + k.opt.np)), 8).nstage >= k.opt.tga &&
          spec_geometry(c, k.maxcols_t, 2, k.tr_t, 0, 8).nstage >= 1;
 }
 
@@ -323,7 +332,7 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
   obs::SpecParams p{};
   spec_fill(p, pl, TR);
   /* the coefficient copy doubles as the scratch of the final residual reduction (one double per thread) */
-  const SpecGeom g = spec_geometry(c, p.ncol, 1, TR, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (warps + k.opt.np)), std::max(2 * k.opt.tga, 3), k.opt.tga);
+  const SpecGeom g = spec_geometry(c, p.ncol, 1, TR, std::max<size_t>(k.vec_bytes_a, 8 * 32 * (warps + k.opt.np)), 8);
   if (g.nstage < k.opt.tga) throw std::logic_error("specialised Phi a does not fit in shared memory");
   p.nstage = g.nstage; p.off_vec = g.off_vec; p.off_tile = g.off_tile; p.tile_doubles = g.tile_doubles; p.off_flags = 128;
   p.out = a.out; p.w = a.w; p.y = a.y; p.sd = a.sd; p.mode = a.mode;

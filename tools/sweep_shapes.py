@@ -1,15 +1,25 @@
+"""Option sweeps of the specialised kernels through bench.py (device-resident timing of Phi a / Phi^T).
+
+  python tools/sweep_shapes.py "OPTS[|bench args]" ...      e.g.  "1,4,2,80,8,1,4,16,56|--config c4share"  "1,2,4|--rows 125000"
+
+OPTS is a prefix of OB_SPEC_OPTS (ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc,qd,tgd,cache_d,maxcols_d,
+nreg_c,nreg_p,psleep); missing fields keep their defaults.  One line per run; results of round 2: profiles/r02_spec_sweeps.txt."""
 import json, os, subprocess, sys
-REPO="/root/repo"
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def run(cfg, extra):
     env = dict(os.environ, OB_SPEC_OPTS=cfg)
-    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "6", "--warmup", "3", "--no-optcg", "--no-cpu-baseline"] + extra, env=env, capture_output=True, text=True, timeout=300)
+    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "6", "--warmup", "3", "--no-optcg", "--no-cpu-baseline"] + extra,
+                       env=env, capture_output=True, text=True, timeout=300)
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])
-        print(" ".join(extra), cfg, "pairs/s %.1f" % d["value"], "phi_a %.4f ms" % d["roofline"]["ms_phi_a"], "phi_t %.4f ms" % d["roofline"]["ms_phi_t"], flush=True)
+        print(" ".join(extra) or "c3", cfg, "pairs/s %.1f" % d["value"], "phi_a %.4f ms" % d["roofline"]["ms_phi_a"], "phi_t %.4f ms" % d["roofline"]["ms_phi_t"], flush=True)
     except Exception:
         print(cfg, "FAILED", p.stderr[-300:], flush=True)
-base="1,4,2,80,8,1,4,16,%d,4,0,1,8,16,2,3,10,96,232,40,128"
-for cap in (56, 72, 92, 112):
-    run(base % cap, ["--config", "c4share"])
-for cfg in ("1,4,2,80,8,1,4,16,56,4,0,1,8,16,2,3,10,96,232,40,128", "1,2,4,80,8,1,4,16,56,4,0,1,8,16,2,3,10,96,232,40,128", "1,4,2,80,8,1,2,16,56,4,0,1,8,16,2,3,10,96,232,40,128", "1,2,4,80,8,1,2,16,56,4,0,1,8,16,2,3,10,96,232,40,128"):
-    run(cfg, ["--rows", "125000"])
+
+
+for arg in sys.argv[1:]:
+    cfg, _, extra = arg.partition("|")
+    run(cfg, extra.split())
