@@ -192,7 +192,9 @@ int ob_outerbase_terms_stats(ob_outerbase* ob, uint64_t* W, uint64_t* Lcols, uin
  * "overlap" 1|0 (env OB_OVERLAP) -- ob_outerbase_mm / _tmm on host buffers of 2^17 rows or more overlap
  * the transfer with the kernel (page-locked result written by the kernel, input vector streamed in
  * on a second stream); 0 = staged copies -- needed under tools that serialise kernels and copies
- * (ncu), where the kernel would wait for rows that cannot arrive (it traps after 20 s). */
+ * (ncu), where the kernel would wait for rows that cannot arrive (it traps after 20 s);
+ * "tmap" 1|0 (env OB_TMAP) -- phi_a_spec stages a row tile with one 2-D tensor copy (cp.async.bulk.tensor) per
+ * dimension of the model instead of one bulk copy per basis column. */
 int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value);
 int ob_outerbase_specialize(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* compile_seconds);
 /* 1: the specialised kernels serve this table, 0: interpreter kernels, -1: not specialisable */

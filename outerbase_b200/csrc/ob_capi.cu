@@ -255,6 +255,7 @@ int ob_ctx_set_option(ob_ctx* ctx, const char* name, double value) {
   else if (n == "dsweep") ctx->c.dsweep = value != 0;
   else if (n == "device_cg") ctx->c.device_cg = value != 0;
   else if (n == "overlap") ctx->c.overlap = value != 0;
+  else if (n == "tmap") ctx->c.tmap = value != 0;
   else if (n == "p2p") ctx->c.p2p.enabled = value != 0; /* same value on every rank */
   else throw std::invalid_argument("unknown option " + n);
   OB_CATCH

@@ -101,6 +101,9 @@ struct Ctx {
   /* host-pointer mm / tmm overlap their transfers with the kernel (option "overlap", env OB_OVERLAP; on by default).
    * Off under tools that serialise kernels and copies (ncu): the kernel would wait for rows that cannot arrive. */
   bool overlap = true;
+  /* phi_a_spec stages its tiles with 2-D tensor copies (option "tmap", env OB_TMAP; on by default): 0 = one bulk copy
+   * per column, as phi_t_spec does */
+  bool tmap = true;
   void fuse_allreduce(size_t n) { fused = false; fuse_n = p2p_ok(n) ? n : 0; }
   void allreduce_after(double* buf_dev, size_t n) {
     fuse_n = 0;
@@ -181,6 +184,10 @@ struct ColTable {
   DevBuf<int> col_op;             /* ncol entries: op | (auxcol << 8) */
   int ncol = 0, nload = 0;
   bool has_ops = false;
+  std::vector<const double*> src_host; /* host image of load_src (tensor maps are encoded from it) */
+  /* 2-D tensor maps of phi_a_spec's tile (one per run of adjacent columns), built at first use for one tile height */
+  mutable DevBuf<unsigned char> tmaps;
+  mutable int tmap_tr = 0, tmap_state = 0; /* 0 not built, 1 ready, -1 unavailable for this table */
 };
 
 /* compiled terms, resident on the device */
@@ -213,6 +220,7 @@ struct PhiPlan {
   const double* scale = nullptr;   /* basescale (N) */
   int sq = 0;                      /* use scale^2 */
   u64 N = 0;
+  u64 ld = 0;                      /* rows every column is allocated with (0: unknown -- no tensor maps) */
 };
 
 struct Workspace {

@@ -442,6 +442,7 @@ struct OuterBase {
     e.ct->has_ops = !aux.empty();
     e.ct->load_src.upload(src, ctx.stream);
     e.ct->col_op.upload(ops, ctx.stream);
+    e.ct->src_host = src;
     ctx.sync();
     coltables.push_front(std::move(e));
     return coltables.front().ct.get();
@@ -449,7 +450,7 @@ struct OuterBase {
 
   obd::PhiPlan plan(const obd::DevProgram* prog, int sq, int h) {
     obd::PhiPlan pl;
-    pl.prog = prog; pl.cols = coltable(prog, sq, h); pl.scale = scale.p; pl.sq = sq; pl.N = N;
+    pl.prog = prog; pl.cols = coltable(prog, sq, h); pl.scale = scale.p; pl.sq = sq; pl.N = N; pl.ld = ld;
     return pl;
   }
 

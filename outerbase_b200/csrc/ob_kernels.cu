@@ -900,6 +900,7 @@ Ctx::Ctx(int dev) : device(dev) {
   if (const char* e = getenv("OB_DSWEEP")) dsweep = std::string(e) != "0";
   if (const char* e = getenv("OB_DEVICE_CG")) device_cg = std::string(e) != "0";
   if (const char* e = getenv("OB_OVERLAP")) overlap = std::string(e) != "0";
+  if (const char* e = getenv("OB_TMAP")) tmap = std::string(e) != "0";
   if (const char* e = getenv("OB_SPEC")) { /* 0 | 1 | auto */
     const std::string v(e);
     spec_mode = v == "0" ? 0 : (v == "1" ? 1 : 2);

@@ -55,6 +55,8 @@ struct SpecParams {
   unsigned long long timeout_ns;
   unsigned sync_target, seq;
   int G, rank, fuse_tail, extra_n;
+  const void* tmaps;             /* Phi a: one 2-D tensor map per run of adjacent basis columns (option tmap), or null:
+                                    one bulk copy per column */
 };
 
 /* mirrored by `struct MatParams` in ob_spec_scaffold.inc (phi_am_spec) */
@@ -125,6 +127,9 @@ struct SpecOptions {
   int nreg_c = 232, nreg_p = 40;
   /* nanoseconds a producer warp sleeps between two polls of a stage's `empty` barrier (0 = poll at full speed) */
   int psleep = 128;
+  /* Phi a stages a tile with one 2-D tensor copy (cp.async.bulk.tensor, SASS UTMALDG) per dimension -- the levels
+   * 1..max of a dimension are adjacent columns of the basis matrix -- instead of one bulk copy per column */
+  int tmap = 0;
 };
 
 struct SpecSource {
@@ -189,9 +194,9 @@ struct Factors {
 };
 
 /* backward (Horner) stream g -> statements accumulating into o[r] */
-inline void emit_bwd(Emitter& e, const Program& P, int g, int R, int TR, int cache) {
+inline void emit_bwd(Emitter& e, const Program& P, int g, int R, int TR, int cache, const std::vector<int>* pos = nullptr) {
   using namespace obt;
-  Factors F(P, P.bwd, P.bwd_off[g], P.bwd_off[g + 1], false, cache, R, TR);
+  Factors F(P, P.bwd, P.bwd_off[g], P.bwd_off[g + 1], false, cache, R, TR, pos);
   int slot = (int)P.slot_base[g] + (int)P.slot_real[g] - 1;
   int nv = 0;
   /* symbolic values: "" = known zero, else a variable stem (stem_r) */
@@ -542,6 +547,28 @@ inline int choose_types(const u64* terms, u64 K, u64 d, const SpecOptions& opt) 
   return 0;
 }
 
+/* Phi a's tile layout: program columns sorted by (dimension, level); a run = consecutive levels of one dimension */
+inline std::vector<int> tile_order(const Program& P) {
+  std::vector<int> order(P.cols.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const obt::ColRef &x = P.cols[a], &y = P.cols[b];
+    if (x.aug != y.aug) return x.aug < y.aug;
+    return x.dim != y.dim ? x.dim < y.dim : x.level < y.level;
+  });
+  return order;
+}
+/* first tile column of every run */
+inline std::vector<int> tile_runs(const Program& P, const std::vector<int>& order) {
+  std::vector<int> runs;
+  for (size_t c = 0; c < order.size(); ++c) {
+    const obt::ColRef& x = P.cols[order[c]];
+    const bool cont = c > 0 && P.cols[order[c - 1]].aug == x.aug && P.cols[order[c - 1]].dim == x.dim && P.cols[order[c - 1]].level + 1 == x.level;
+    if (!cont) runs.push_back((int)c);
+  }
+  return runs;
+}
+
 /* pa: program compiled with G = 1 (or null: no Phi a kernel); pt: G = types * opt.wt (or null) */
 inline SpecSource generate(const Program* pa, const Program* pt, int types, const SpecOptions& opt) {
   using namespace detail;
@@ -572,14 +599,25 @@ inline SpecSource generate(const Program* pa, const Program* pt, int types, cons
     const Program& P = *pa;
     hdr.f("#define OBS_HAVE_A 1\n#define OBS_RA %d\n#define OBS_QA %d\n#define OBS_TGA %d\n#define OBS_NCOLS_A %d\n", opt.ra, opt.qa,
           opt.tga, (int)P.cols.size());
+    /* tile columns in (dimension, level) order: the levels of one dimension are adjacent columns of the basis matrix,
+     * so a run of them is ONE 2-D tensor copy (tile_runs) */
+    std::vector<int> order = tile_order(P);
+    if (!opt.tmap) for (size_t c = 0; c < order.size(); ++c) order[c] = (int)c; /* bulk copies: the program's own (hottest first) order */
+    std::vector<int> pos(P.cols.size());
+    for (size_t c = 0; c < order.size(); ++c) pos[order[c]] = (int)c;
     tab.f("__device__ const unsigned short obs_cols_a[] = {");
-    for (size_t c = 0; c < P.cols.size(); ++c) tab.f("%d,", (int)c);
+    for (size_t c = 0; c < order.size(); ++c) tab.f("%d,", order[c]);
     tab.f("0};\n");
+    const std::vector<int> runs = tile_runs(P, order);
+    hdr.f("#define OBS_TMAP_A %d\n#define OBS_NRUNS_A %d\n", (opt.tmap && runs.size() <= 31) ? 1 : 0, (int)runs.size());
+    tab.f("__device__ const unsigned short obs_run_col_a[] = {");
+    for (int r : runs) tab.f("%d,", r);
+    tab.f("%d};\n", (int)order.size());
     /* machine-readable layout (comments): tile column -> (dimension, level), coefficient slot -> term */
-    for (size_t c = 0; c < P.cols.size(); ++c) tab.f("// OBS_LAYOUT_A %d %u %u\n", (int)c, P.cols[c].dim, P.cols[c].level);
+    for (size_t c = 0; c < order.size(); ++c) tab.f("// OBS_LAYOUT_A %d %u %u\n", (int)c, P.cols[order[c]].dim, P.cols[order[c]].level);
     for (u64 i = 0; i < P.nslots(); ++i) tab.f("// OBS_SLOT_A %d %d\n", (int)i, (int)P.slot_term[i]);
     ca.f("/*BEGIN_BODY_A*/\n");
-    emit_bwd(ca, P, 0, opt.ra, S.tr_a, opt.cache_a);
+    emit_bwd(ca, P, 0, opt.ra, S.tr_a, opt.cache_a, &pos);
     ca.f("/*END_BODY_A*/\n");
   }
   if (want_t) {

@@ -10,6 +10,7 @@
  * are cached on disk by source hash ($OB_SPEC_CACHE, default ~/.cache/outerbase_b200;
  * "0" disables) because a compile takes seconds.
  */
+#include <cuda.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -191,11 +192,11 @@ struct SpecKernels {
 
 obs::SpecOptions spec_default_options() {
   obs::SpecOptions o;
-  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc,qd,tgd,cache_d,maxcols_d,nreg_c,nreg_p,psleep -- tuning only */
+  if (const char* e = getenv("OB_SPEC_OPTS")) { /* ra,qa,tga,cache_a,wt,rt,pt,cache_t,acc_cap,np,mc,ut,mw,kc,qd,tgd,cache_d,maxcols_d,nreg_c,nreg_p,psleep,tmap -- tuning only */
     int* f[] = {&o.ra, &o.qa, &o.tga, &o.cache_a, &o.wt, &o.rt, &o.pt, &o.cache_t, &o.acc_cap, &o.np, &o.mc, &o.ut, &o.mw, &o.kc,
-                &o.qd, &o.tgd, &o.cache_d, &o.maxcols_d, &o.nreg_c, &o.nreg_p, &o.psleep};
+                &o.qd, &o.tgd, &o.cache_d, &o.maxcols_d, &o.nreg_c, &o.nreg_p, &o.psleep, &o.tmap};
     int i = 0;
-    for (const char* p = e; *p && i < 21; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (const char* p = e; *p && i < 22; ++i) { *f[i] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
   }
   return o;
 }
@@ -236,6 +237,59 @@ bool device_range_readable(const void* p, size_t bytes) {
   return lo >= base && lo + bytes <= base + size;
 }
 double spec_compile_seconds(const SpecKernels& k) { return k.from_cache ? 0.0 : k.compile_seconds; }
+
+/* ---- 2-D tensor maps of phi_a_spec's tile (option tmap).  The tile's columns are ordered by (dimension, level); the
+ * levels 1..max of a dimension are adjacent columns of the (compact) basis matrix, so each such run is ONE tiled tensor
+ * copy of TR rows x run-length columns instead of run-length bulk copies.  Encoded through the driver entry point (no
+ * link against libcuda); any table whose runs are not evenly strided in memory keeps the bulk copies. */
+using TensorMap128 = CUtensorMap;
+static_assert(sizeof(CUtensorMap) == 128, "the kernel indexes the maps 128 bytes apart");
+static bool encode_tile_map(TensorMap128* out, const double* base, u64 rows, u64 width, u64 stride_bytes, int TR) {
+  using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<Fn>(f);
+  }
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {rows, width};
+  const cuuint64_t gstride[1] = {stride_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)TR, (cuuint32_t)width};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2u, const_cast<double*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static const void* tile_tensor_maps(Ctx& c, const SpecKernels& k, const PhiPlan& pl, int TR) {
+  const ColTable& ct = *pl.cols;
+  if (ct.tmap_state == 1 && ct.tmap_tr == TR) return ct.tmaps.p;
+  if (ct.tmap_state == -1) return nullptr;
+  ct.tmap_state = -1;
+  const obt::Program& P = k.pa_host;
+  if (pl.ld == 0 || pl.ld % (u64)TR || pl.N >= (1ull << 31) || ct.src_host.size() < P.cols.size() || ct.nload != ct.ncol) return nullptr;
+  if (!k.opt.tmap) return nullptr; /* the module's tile is in the program's column order */
+  const std::vector<int> order = obs::tile_order(P), runs = obs::tile_runs(P, order);
+  if (runs.empty() || runs.size() > 31) return nullptr;
+  std::vector<TensorMap128> maps(runs.size());
+  for (size_t r = 0; r < runs.size(); ++r) {
+    const int c0 = runs[r], c1 = r + 1 < runs.size() ? runs[r + 1] : (int)order.size();
+    const double* base = ct.src_host[order[c0]];
+    for (int cc = c0 + 1; cc < c1; ++cc) /* adjacent columns, ld rows apart */
+      if (ct.src_host[order[cc]] != base + (size_t)(cc - c0) * pl.ld) return nullptr;
+    if ((uintptr_t)base % 16 || c1 - c0 > 256) return nullptr;
+    if (!encode_tile_map(&maps[r], base, pl.ld, (u64)(c1 - c0), pl.ld * sizeof(double), TR)) return nullptr;
+  }
+  ct.tmaps.ensure(maps.size() * sizeof(TensorMap128));
+  OB_CUDA(cudaMemcpyAsync(ct.tmaps.p, maps.data(), maps.size() * sizeof(TensorMap128), cudaMemcpyHostToDevice, c.stream));
+  OB_CUDA(cudaStreamSynchronize(c.stream)); /* `maps` is a local */
+  ct.tmap_tr = TR;
+  ct.tmap_state = 1;
+  return ct.tmaps.p;
+}
 
 static void spec_fill(obs::SpecParams& p, const PhiPlan& pl, int TR) {
   p.load_src = pl.cols->load_src.p; p.col_op = pl.cols->col_op.p;
@@ -340,6 +394,7 @@ void launch_phi_a_spec(Ctx& c, SpecKernels& k, const PhiPlan& pl, const PhiAArgs
   if (a.mode == PHI_UPDATE || a.mode == PHI_DOT) p.ssq_partial = a.ssq_partial ? a.ssq_partial : ws.ssq.ensure(c.sms);
   if (a.mode == PHI_DOT) { p.win = a.wdot; p.yh = a.yh; }
   p.a = a.a; p.slot_term = pl.prog->slot_term.p; p.nslots = (int)pl.prog->host.nslots();
+  p.tmaps = (k.opt.tmap && c.tmap) ? tile_tensor_maps(c, k, pl, TR) : nullptr;
   spec_launch(c, k.ka, k.smem_a_set, grid, 32 * (warps + k.opt.np), g.smem, p, "phi_a_spec");
   if (grid_out) *grid_out = grid;
 }

@@ -250,6 +250,46 @@ print("multicast OK", info)
     assert res.returncode == 0 and "multicast OK" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
 
 
+def test_tensor_map_staging_variant_parity(oracle):
+    """Option tmap: phi_a_spec stages a row tile with one 2-D tensor copy (cp.async.bulk.tensor / UTMALDG) per dimension
+    instead of one bulk copy per column -- generated in a fresh process (the options are read when a module is generated),
+    plain and squared operators, ragged row counts, against the oracle and bit for bit against the bulk-copy staging."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+from conftest import make_problem, relerr, ORACLE_LIB
+from outerbase_b200.binding import Library
+import outerbase_b200 as obp
+gpu = obp.lib(0)
+gpu.set_option("spec", 1)
+oracle = Library(ORACLE_LIB, "orc_")
+for N, K in ((3000, 200), (64, 30), (12345, 777)):
+    om, x, y, terms, rng = make_problem(oracle, N, K)
+    ob = oracle.outerbase(om, x)
+    omg, *_ = make_problem(gpu, N, K)
+    obg = gpu.outerbase(omg, x)
+    src, info = gpu.spec_source(terms)
+    assert "#define OBS_TMAP_A 1" in src and "cp.async.bulk.tensor.2d" in src
+    a = rng.normal(size=K)
+    n0 = gpu.launch_count()
+    y1, s1 = obg.matmul(terms, a), obg.sqmm(terms, np.abs(a))
+    assert gpu.launch_count() >= n0 + 2
+    assert relerr(y1, ob.matmul(terms, a)) < 1e-12 and relerr(s1, ob.sqmm(terms, np.abs(a))) < 1e-12
+    gpu.set_option("tmap", 0)  # same module, one bulk copy per column
+    np.testing.assert_array_equal(obg.matmul(terms, a), y1)
+    np.testing.assert_array_equal(obg.sqmm(terms, np.abs(a)), s1)
+    gpu.set_option("tmap", 1)
+print("tensor maps OK")
+'''
+    env = dict(os.environ, OB_SPEC_OPTS="1,2,4,80,8,1,4,16,56,4,0,1,8,16,2,3,10,96,232,40,128,1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                         cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    assert res.returncode == 0 and "tensor maps OK" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
+
+
 @pytest.mark.parametrize("N,K,C", [(300, 60, 8), (1000, 200, 20), (4000, 500, 64), (777, 150, 70)])
 def test_multi_rhs_tensor_core_kernel(spec, oracle, N, K, C):
     """prodmm_(mat) (linalg.cpp:527-557) as one dense contraction on the FP64 tensor cores (phi_am_spec, DMMA):

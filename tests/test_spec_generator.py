@@ -38,6 +38,27 @@ def test_options_and_multicast_variant_compile(product_symbols):
         product_symbols.spec_source(terms, [1, 3, 2, 16, 8, 1, 4, 8, 32])  # 96-row tiles do not divide the row padding
 
 
+def test_tensor_map_variant_layout_and_compile(product_symbols, monkeypatch):
+    """Option tmap (22nd field of OB_SPEC_OPTS): Phi a's tile columns are ordered by (dimension, level), so that the levels
+    of a dimension -- adjacent columns of the basis matrix -- are one 2-D tensor copy; the run table lists their first
+    tile columns; the module compiles for sm_100a."""
+    import re
+    terms, _ = _terms(product_symbols, 300)
+    monkeypatch.setenv("OB_SPEC_OPTS", "1,2,4,80,8,1,4,16,56,4,0,1,8,16,2,3,10,96,232,40,128,1")
+    src, info = product_symbols.spec_source(terms)
+    assert "#define OBS_TMAP_A 1" in src
+    layout = [tuple(int(v) for v in m) for m in re.findall(r"// OBS_LAYOUT_A (\d+) (\d+) (\d+)", src)]
+    assert [c for c, _, _ in layout] == list(range(len(layout)))
+    assert [(d, l) for _, d, l in layout] == sorted((d, l) for _, d, l in layout)
+    runs = [int(v) for v in re.search(r"obs_run_col_a\[\] = \{([\d,]+)\}", src).group(1).split(",")]
+    starts = [c for c, d, l in layout if c == 0 or (layout[c - 1][1], layout[c - 1][2] + 1) != (d, l)]
+    assert runs == starts + [len(layout)] and int(re.search(r"#define OBS_NRUNS_A (\d+)", src).group(1)) == len(starts)
+    product_symbols.spec_compile_check(src)
+    monkeypatch.delenv("OB_SPEC_OPTS")
+    src0, _ = product_symbols.spec_source(terms)
+    assert "#define OBS_TMAP_A 0" in src0
+
+
 HARNESS = r"""
 #include <cmath>
 #include <cstdint>

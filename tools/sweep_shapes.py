@@ -11,8 +11,12 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(cfg, extra):
     env = dict(os.environ, OB_SPEC_OPTS=cfg)
-    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "6", "--warmup", "3", "--no-optcg", "--no-cpu-baseline"] + extra,
-                       env=env, capture_output=True, text=True, timeout=300)
+    try:
+        p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "6", "--warmup", "3", "--no-optcg", "--no-cpu-baseline"] + extra,
+                           env=env, capture_output=True, text=True, timeout=150)
+    except subprocess.TimeoutExpired:
+        print(" ".join(extra) or "c3", cfg, "TIMEOUT", flush=True)
+        return
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])
         print(" ".join(extra) or "c3", cfg, "pairs/s %.1f" % d["value"], "phi_a %.4f ms" % d["roofline"]["ms_phi_a"], "phi_t %.4f ms" % d["roofline"]["ms_phi_t"], flush=True)
