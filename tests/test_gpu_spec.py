@@ -277,7 +277,7 @@ for N, K in ((3000, 200), (64, 30), (12345, 777)):
     n0 = gpu.launch_count()
     y1, s1 = obg.matmul(terms, a), obg.sqmm(terms, np.abs(a))
     assert gpu.launch_count() >= n0 + 2
-    assert relerr(y1, ob.matmul(terms, a)) < 1e-12 and relerr(s1, ob.sqmm(terms, np.abs(a))) < 1e-12
+    assert relerr(y1, ob.matmul(terms, a)) < 1e-9 and relerr(s1, ob.sqmm(terms, np.abs(a))) < 1e-9  # each side on its own basis build
     gpu.set_option("tmap", 0)  # same module, one bulk copy per column
     np.testing.assert_array_equal(obg.matmul(terms, a), y1)
     np.testing.assert_array_equal(obg.sqmm(terms, np.abs(a)), s1)
