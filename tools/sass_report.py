@@ -61,14 +61,22 @@ O = Library(REPO / "oracle" / "_build" / "libob_oracle.so", "orc_")
 om, terms = bench.setup_model(O)
 lib = ob.load_symbols_only()
 d = Path(tempfile.mkdtemp())
-for tag, src in (("main", lib.spec_source(terms)[0]), ("dot", lib.spec_source_dot(terms)[0])):
-    (d / f"{tag}.cu").write_text(src)
-    subprocess.run(["nvcc", "-arch=sm_100a", "-cubin", "-lineinfo", "-std=c++17", "-o", str(d / f"{tag}.cubin"), str(d / f"{tag}.cu")], check=True, capture_output=True)
-    s2 = subprocess.run(["cuobjdump", "-sass", str(d / f"{tag}.cubin")], capture_output=True, text=True).stdout
+import os
+os.environ["OB_SPEC_OPTS"] = "1,2,4,80,8,1,4,16,56,4,0,1,8,16,2,3,10,96,232,40,128,1"
+src_tmap = lib.spec_source(terms)[0]
+del os.environ["OB_SPEC_OPTS"]
+for tag, src in (("main", lib.spec_source(terms)[0]), ("dot", lib.spec_source_dot(terms)[0]), ("mat", lib.spec_source_mat(terms)[0]),
+                 ("tmat", lib.spec_source_tmat(terms)[0]), ("main, option tmap = 1", src_tmap)):
+    stem = re.sub(r"\W+", "_", tag)
+    (d / f"{stem}.cu").write_text(src)
+    subprocess.run(["nvcc", "-arch=sm_100a", "-cubin", "-lineinfo", "-std=c++17", "-o", str(d / f"{stem}.cubin"), str(d / f"{stem}.cu")], check=True, capture_output=True)
+    s2 = subprocess.run(["cuobjdump", "-sass", str(d / f"{stem}.cubin")], capture_output=True, text=True).stdout
     f2 = functions(s2)
     print(f"\n## run-time generated module `{tag}` for the C3 terms table (d=10, K=2000; same source NVRTC compiles on the GPU box, here through nvcc -arch=sm_100a)\n")
     table(f2)
     for k, v in f2.items():
+        if "tmap" in tag and k != "phi_a_spec":
+            continue
         if k == "phi_t_spec":
             excerpt(v, r"USETMAXREG", 3, 4, "`phi_t_spec`: warp-specialised register split (setmaxnreg)")
             excerpt(v, r"UBLKCP", 8, 6, "`phi_t_spec` producer: one bulk copy (TMA engine) per staged column")
@@ -77,6 +85,15 @@ for tag, src in (("main", lib.spec_source(terms)[0]), ("dot", lib.spec_source_do
             print("\n`phi_t_spec`: one stream's pass loop (register accumulators, one per term)\n```")
             print("\n".join(v[i - 20:i + 25]))
             print("```")
+        if k == "phi_a_spec" and "tmap" in tag:
+            excerpt(v, r"UTMALDG", 10, 6, "`phi_a_spec`, option tmap: one 2-D tensor copy per run of adjacent basis columns")
+            continue
+        if k == "phi_am_spec":
+            excerpt(v, r"DMMA", 14, 10, "`phi_am_spec`: fragment loads and the FP64 tensor-core contraction of one block")
+        if k == "phi_tm_spec":
+            excerpt(v, r"DMMA", 14, 10, "`phi_tm_spec`: contraction over the rows of a pass")
+        if k == "phi_t_spec" and "tmap" in tag:
+            continue
         if k == "phi_a_spec":
             dl = [i for i, l in enumerate(v) if "DFMA" in l]
             i = dl[len(dl) // 2]
