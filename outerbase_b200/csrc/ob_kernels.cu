@@ -1092,15 +1092,37 @@ const unsigned* Ctx::stream_rows_begin() {
   return rows_ready;
 }
 
+/* cuStreamWriteValue32 through the runtime's driver entry point: publishes the arrived-row count in stream order
+ * without a second DMA transfer per chunk (falls back to a 4-byte copy) */
+static bool stream_write_u32(cudaStream_t st, unsigned* dev, unsigned value) {
+  using Fn = int (*)(cudaStream_t, unsigned long long, unsigned, unsigned);
+  static Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (!getenv("OB_OVERLAP_NOWRITEVALUE") &&
+        cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<Fn>(f);
+  }
+  return fn && fn(st, (unsigned long long)(uintptr_t)dev, value, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT */) == 0;
+}
+
 void Ctx::stream_rows_copy(double* dst, const double* src, size_t n) {
-  const size_t chunks = std::min<size_t>(16, std::max<size_t>(1, n / 65536));
+  /* chunks: enough for the kernel to start on the first rows early, few enough that the fixed cost per DMA transfer
+   * (several microseconds) stays below the kernel's own time (OB_OVERLAP_CHUNKS, tools/e2e_probe.py) */
+  static const size_t want = [] { const char* e = getenv("OB_OVERLAP_CHUNKS"); return e ? (size_t)std::max(1, atoi(e)) : (size_t)16; }();
+  const size_t chunks = std::min<size_t>(std::min<size_t>(want, 64), std::max<size_t>(1, n / 65536));
   const size_t per = ((n + chunks - 1) / chunks + 2047) / 2048 * 2048;
   size_t c = 0;
   for (size_t r0 = 0; r0 < n; r0 += per, ++c) {
     const size_t r1 = std::min(n, r0 + per);
     OB_CUDA(cudaMemcpyAsync(dst + r0, src + r0, (r1 - r0) * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
-    rows_table[c] = (unsigned)r1;
-    OB_CUDA(cudaMemcpyAsync(rows_ready, rows_table + c, sizeof(unsigned), cudaMemcpyHostToDevice, copy_stream));
+    if (!stream_write_u32(copy_stream, rows_ready, (unsigned)r1)) {
+      rows_table[c] = (unsigned)r1;
+      OB_CUDA(cudaMemcpyAsync(rows_ready, rows_table + c, sizeof(unsigned), cudaMemcpyHostToDevice, copy_stream));
+    }
   }
   OB_CUDA(cudaEventRecord(ev_copy, copy_stream));
 }
