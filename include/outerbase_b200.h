@@ -134,6 +134,8 @@ int ob_outerbase_loopvals(ob_outerbase* ob, uint64_t* nthreads, uint64_t* chunks
 int ob_outerbase_get_real(ob_outerbase* ob, const char* which, double* out, uint64_t* nrow, uint64_t* ncol);
 int ob_outerbase_getbase(ob_outerbase* ob, uint64_t dim_1based, double* out /* N x m_dim */);
 int ob_outerbase_getmat(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out /* N x K */);
+/* outerbase::getmat_gradhyp, src/modandbase.cpp:663-669 (C++ only, loglik_std's cube): N x K x H, slice after slice */
+int ob_outerbase_getmat_gradhyp(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out /* N x K x H */);
 /* sq != 0 selects the squared operators (basematsq/basescalesq). */
 int ob_outerbase_mm(ob_outerbase* ob, int sq, const uint64_t* terms, uint64_t K,
                     const double* a /* K */, double* out /* N */);
@@ -232,9 +234,10 @@ int ob_debug_terms_eval(const uint64_t* terms, uint64_t K, uint64_t d, const uin
                         uint64_t* stats /* W, Lcols, nodes, maxdepth, fast_ok, nslots, nwords_fwd, nwords_bwd */);
 
 /* ------------------------------------------------------------------ stateless linalg.h seam
- * Exactly the eight free functions of src/linalg.h:9-58 minus getmge_ (broken in
- * the reference, linalg.cpp:788-810): same argument meaning, host buffers,
- * basemat is N x M column-major.  vertpl/chunksize/loopsize/num_threads are
+ * Exactly the eight free functions of src/linalg.h:9-58: same argument meaning, host
+ * buffers, basemat is N x M column-major.  getmge_ follows the reference's unchunked
+ * branch for every shape (its row-chunked branch, linalg.cpp:788-810, cannot work:
+ * dogetmge_ resizes the whole cube to one chunk and the chunk is never copied back).  vertpl/chunksize/loopsize/num_threads are
  * accepted and ignored.  These upload, run the same CUDA kernels, download. */
 int ob_prodmm_vec(ob_ctx* ctx, double* out, const uint64_t* terms, uint64_t K, uint64_t d,
                   const double* a, const double* basemat, uint64_t N, uint64_t M,
@@ -261,6 +264,12 @@ int ob_tprodmmge(ob_ctx* ctx, double* out, double* outge, const uint64_t* terms,
 int ob_getm(ob_ctx* ctx, double* out, const uint64_t* terms, uint64_t K, uint64_t d,
             const double* basemat, uint64_t N, uint64_t M,
             const double* basescale, const uint64_t* knotptst);
+/* getmge_, src/linalg.cpp:724-822: outge is N x K x H (one slice per hyper-parameter). */
+int ob_getmge(ob_ctx* ctx, double* outge, const uint64_t* terms, uint64_t K, uint64_t d,
+              const double* basemat, uint64_t N, uint64_t M,
+              const double* basescale, const uint64_t* knotptst,
+              const double* basematge, uint64_t Mge, const uint64_t* gest,
+              const uint64_t* hypmatch, uint64_t H);
 
 /* ------------------------------------------------------------------ lpdf family
  * loglik_gauss  src/lpdfs/loglik_gauss.cpp:41-179   (device)

@@ -95,8 +95,13 @@ void getm_(mat& out, const umat& terms, const mat& basemat, const vec& basescale
   chk(ob_getm(ctx(), out.memptr(), u64p(terms), terms.n_rows, terms.n_cols, basemat.memptr(), basemat.n_rows, basemat.n_cols,
               basescale.memptr(), u64p(knotptst)));
 }
-/* src/linalg.cpp:778-822 -- explicit d(Phi)/d(hyp) cube, used by loglik_std only; its row-chunk branch is broken upstream
- * (:788-810 copies a zero matrix into the cube) and the C ABI does not provide it */
-void getmge_(cube&, const umat&, const mat&, const vec&, const uvec&, const mat&, const uvec&, const uvec&, bool, uword, uword, int) {
-  throw std::logic_error("getmge_ (loglik_std's explicit gradient cube) is outside the outerbase_b200 hot path");
+/* src/linalg.cpp:778-822 -- explicit d(Phi)/d(hyp) cube, used by loglik_std only.  The ABI follows the unchunked branch for
+ * every shape (the row-chunk branch, :788-810, cannot work upstream: dogetmge_ resizes the whole cube to one chunk and
+ * the chunk is never copied back) */
+void getmge_(cube& outge, const umat& terms, const mat& basemat, const vec& basescale, const uvec& knotptst, const mat& basematge,
+             const uvec& gest, const uvec& hypmatch, bool, uword, uword, int) {
+  const uword H = gest.n_elem - 1;
+  if (outge.n_rows != basemat.n_rows || outge.n_cols != terms.n_rows || outge.n_slices != H) outge.set_size(basemat.n_rows, terms.n_rows, H);
+  chk(ob_getmge(ctx(), outge.memptr(), u64p(terms), terms.n_rows, terms.n_cols, basemat.memptr(), basemat.n_rows, basemat.n_cols,
+                basescale.memptr(), u64p(knotptst), basematge.memptr(), basematge.n_cols, u64p(gest), u64p(hypmatch), H));
 }

@@ -793,6 +793,8 @@ template <class T> struct Cube : arma_tag {
   Cube& zeros() { std::fill(store.begin(), store.end(), T(0)); return *this; }
   Mat<T>& slice(uword s) { shim_check(s < n_slices, "Cube::slice(): index out of bounds"); return views[s]; }
   const Mat<T>& slice(uword s) const { shim_check(s < n_slices, "Cube::slice(): index out of bounds"); return views[s]; }
+  T* memptr() { return store.data(); }
+  const T* memptr() const { return store.data(); }
   Cube& operator+=(const Cube& o) { shim_check(o.n_elem == n_elem, "Cube: incompatible dimensions"); for (uword i = 0; i < n_elem; ++i) store[i] += o.store[i]; return *this; }
   struct slices_view {
     Cube& c; uword a, b;

@@ -1064,9 +1064,11 @@ mat outerbase::getbase(u64 dim) const { /* :634-639 */
   return out;
 }
 mat outerbase::getmat(const umat& terms) const { mat o; getm_(o, terms, basemat, basescale, knotptst, lv()); return o; }
-std::vector<mat> outerbase::getmat_gradhyp(const umat& terms) const { /* :663-669 ; dogetmge_ linalg.cpp:741-750 ; getmge_ :819-821 */
+/* getmge_ / dogetmge_, linalg.cpp:724-822, unchunked branch (the chunked one cannot work, see ob_oracle.hpp) */
+void getmge_(std::vector<mat>& outge, const umat& terms, const mat& basemat, const vec& basescale, const std::vector<u64>& knotptst,
+             const mat& basematge, const std::vector<u64>& gest, const std::vector<u64>& hypmatch) {
   const u64 N = basemat.nr, K = terms.nr, H = gest.size() - 1;
-  std::vector<mat> outge(H, mat(N, K));
+  outge.assign(H, mat(N, K));
   vec tempalt(N);
   for (u64 k = 0; k < K; ++k)
     for (u64 l = 0; l < H; ++l) {
@@ -1076,7 +1078,7 @@ std::vector<mat> outerbase::getmat_gradhyp(const umat& terms) const { /* :663-66
           const double* c = basemat.col(knotptst[m] + terms(k, m));
           for (u64 i = 0; i < N; ++i) tempalt[i] *= c[i];
         }
-      const double* g = basemat_gradhyp.col(gest[l] + terms(k, hypmatch[l]));
+      const double* g = basematge.col(gest[l] + terms(k, hypmatch[l]));
       double* o = outge[l].col(k);
       for (u64 i = 0; i < N; ++i) o[i] = tempalt[i] * g[i];
     }
@@ -1085,6 +1087,10 @@ std::vector<mat> outerbase::getmat_gradhyp(const umat& terms) const { /* :663-66
       double* o = outge[l].col(k);
       for (u64 i = 0; i < N; ++i) o[i] *= basescale[i];
     }
+}
+std::vector<mat> outerbase::getmat_gradhyp(const umat& terms) const { /* :663-669 */
+  std::vector<mat> outge;
+  getmge_(outge, terms, basemat, basescale, knotptst, basemat_gradhyp, gest, hypmatch);
   return outge;
 }
 void outerbase::mm(vec& out, const umat& terms, const vec& a) const { prodmm_(out, terms, a, basemat, basescale, knotptst, lv()); }

@@ -135,6 +135,8 @@ void tprodmm_mat_(mat& out, const umat& terms, const mat& a, const mat& basemat,
                   const std::vector<u64>& knotptst, const loopvals& lv);
 void getm_(mat& out, const umat& terms, const mat& basemat, const vec& basescale,
            const std::vector<u64>& knotptst, const loopvals& lv);
+void getmge_(std::vector<mat>& outge, const umat& terms, const mat& basemat, const vec& basescale, const std::vector<u64>& knotptst,
+             const mat& basematge, const std::vector<u64>& gest, const std::vector<u64>& hypmatch);
 
 /* ---- outerbase: src/modandbase.h:57-125, src/modandbase.cpp:459-922 ---- */
 struct outerbase {

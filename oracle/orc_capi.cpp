@@ -224,6 +224,13 @@ int orc_outerbase_getbase(orc_outerbase* ob, uint64_t dim, double* out) {
   std::copy(m.a.begin(), m.a.end(), out);
   ORC_CATCH
 }
+int orc_outerbase_getmat_gradhyp(orc_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
+  ORC_TRY
+  std::vector<mat> g = ob->ob->getmat_gradhyp(to_umat(terms, K, ob->ob->d));
+  uint64_t off = 0;
+  for (const mat& m : g) { std::copy(m.a.begin(), m.a.end(), out + off); off += m.a.size(); }
+  ORC_CATCH
+}
 int orc_outerbase_getmat(orc_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
   ORC_TRY
   mat m = ob->ob->getmat(to_umat(terms, K, ob->ob->d));
@@ -384,6 +391,16 @@ int orc_getm(orc_ctx*, double* out, const uint64_t* terms, uint64_t K, uint64_t 
   mat o;
   getm_(o, to_umat(terms, K, d), to_mat(basemat, N, M), vec(basescale, basescale + N), kp(knotptst, d + 1), default_lv(N));
   std::copy(o.a.begin(), o.a.end(), out);
+  ORC_CATCH
+}
+int orc_getmge(orc_ctx*, double* outge, const uint64_t* terms, uint64_t K, uint64_t d, const double* basemat, uint64_t N, uint64_t M,
+               const double* basescale, const uint64_t* knotptst, const double* basematge, uint64_t Mge, const uint64_t* gest,
+               const uint64_t* hypmatch, uint64_t H) {
+  ORC_TRY
+  std::vector<mat> g;
+  getmge_(g, to_umat(terms, K, d), to_mat(basemat, N, M), vec(basescale, basescale + N), kp(knotptst, d + 1), to_mat(basematge, N, Mge),
+          kp(gest, H + 1), kp(hypmatch, H));
+  for (uint64_t h = 0; h < g.size(); ++h) std::copy(g[h].a.begin(), g[h].a.end(), outge + h * N * K);
   ORC_CATCH
 }
 

@@ -296,6 +296,12 @@ int ref_outerbase_getbase(ref_outerbase* ob, uint64_t dim, double* out) {
   put(ob->ob->getbase(dim), out);
   REF_CATCH
 }
+int ref_outerbase_getmat_gradhyp(ref_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) {
+  REF_TRY
+  cube g = ob->ob->getmat_gradhyp(to_umat(terms, K, ob->ob->d));
+  std::copy(g.store.begin(), g.store.end(), out);
+  REF_CATCH
+}
 int ref_outerbase_getmat(ref_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) { REF_TRY put(ob->ob->getmat(to_umat(terms, K, ob->ob->d)), out); REF_CATCH }
 static void mm_impl(const outerbase& ob, int sq, const umat& t, const double* a, double* out) {
   vec o;
@@ -430,6 +436,17 @@ int ref_tprodmmge(ref_ctx*, double* out, double* outge, const uint64_t* terms, u
   tprodmmge_(o, g, to_umat(terms, K, d), to_vec(a, N), to_mat(basemat, N, M), to_vec(basescale, N), to_uvec(knotptst, d + 1), to_mat(basematge, N, Mge),
              to_uvec(gest, H + 1), to_uvec(hypmatch, H), lv.vertpl, lv.chunksize, lv.loopsize, lv.nthreads);
   put(o, out); put(g, outge);
+  REF_CATCH
+}
+int ref_getmge(ref_ctx*, double* outge, const uint64_t* terms, uint64_t K, uint64_t d, const double* basemat, uint64_t N, uint64_t M, const double* basescale,
+               const uint64_t* knotptst, const double* basematge, uint64_t Mge, const uint64_t* gest, const uint64_t* hypmatch, uint64_t H) {
+  REF_TRY
+  const loopvals lv = default_lv(N);
+  cube g;
+  /* the reference's function as it is; callers keep to unchunked shapes (its chunked branch cannot work, linalg.cpp:788-810) */
+  getmge_(g, to_umat(terms, K, d), to_mat(basemat, N, M), to_vec(basescale, N), to_uvec(knotptst, d + 1), to_mat(basematge, N, Mge), to_uvec(gest, H + 1),
+          to_uvec(hypmatch, H), lv.vertpl, lv.chunksize, lv.loopsize, lv.nthreads);
+  std::copy(g.store.begin(), g.store.end(), outge);
   REF_CATCH
 }
 int ref_getm(ref_ctx*, double* out, const uint64_t* terms, uint64_t K, uint64_t d, const double* basemat, uint64_t N, uint64_t M, const double* basescale,

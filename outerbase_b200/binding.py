@@ -268,6 +268,16 @@ class Library:
     def tprodmmge(self, terms, a, basemat, basescale, knotptst, basematge, gest, hypmatch):
         return self._ge("tprodmmge", terms, a, basemat, basescale, knotptst, basematge, gest, hypmatch, np.asarray(terms).shape[0])
 
+    def getmge(self, terms, basemat, basescale, knotptst, basematge, gest, hypmatch):
+        """getmge_, src/linalg.cpp:778-822: N x K x H cube."""
+        t, bm, bs, bg = _terms(terms), _f64(basemat), _f64(basescale), _f64(basematge)
+        kp, ge, hm = (np.ascontiguousarray(v, dtype=np.uint64) for v in (knotptst, gest, hypmatch))
+        N, M = bm.shape
+        out = np.empty((N, t.shape[0], hm.size), order="F")
+        self.call("getmge", self.ctx, _p(out), _p(t), _u(t.shape[0]), _u(t.shape[1]), _p(bm), _u(N), _u(M), _p(bs), _p(kp), _p(bg), _u(bg.shape[1]),
+                  _p(ge), _p(hm), _u(hm.size))
+        return out
+
     def getm(self, terms, basemat, basescale, knotptst):
         t, bm, bs = _terms(terms), _f64(basemat), _f64(basescale)
         kp = np.ascontiguousarray(knotptst, dtype=np.uint64)
@@ -451,6 +461,13 @@ class outerbase(_Handle):
         t = _terms(terms)
         out = np.empty((self.n_row, t.shape[0]), order="F")
         self._lib.call("outerbase_getmat", self._h, _p(t), _u(t.shape[0]), _p(out))
+        return out
+
+    def getmat_gradhyp(self, terms):
+        """outerbase::getmat_gradhyp, src/modandbase.cpp:663-669: N x K x H cube (loglik_std's basismat_gradhyp)."""
+        t = _terms(terms)
+        out = np.empty((self.n_row, t.shape[0], self._om.sizes()[1]), order="F")
+        self._lib.call("outerbase_getmat_gradhyp", self._h, _p(t), _u(t.shape[0]), _p(out))
         return out
 
     def _mm(self, sq, terms, a, out=None):

@@ -191,6 +191,7 @@ int ob_outerbase_get_real(ob_outerbase* ob, const char* which, double* out, uint
 }
 int ob_outerbase_getbase(ob_outerbase* ob, uint64_t dim, double* out) { OB_TRY ob->ob->getbase(dim, out); OB_CATCH }
 int ob_outerbase_getmat(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) { OB_TRY ob->ob->getmat(terms, K, out); OB_CATCH }
+int ob_outerbase_getmat_gradhyp(ob_outerbase* ob, const uint64_t* terms, uint64_t K, double* out) { OB_TRY ob->ob->getmat_gradhyp(terms, K, out); OB_CATCH }
 int ob_outerbase_mm(ob_outerbase* ob, int sq, const uint64_t* terms, uint64_t K, const double* a, double* out) {
   OB_TRY ob->ob->mm(sq, terms, K, a, out); OB_CATCH
 }
@@ -403,6 +404,11 @@ int ob_tprodmmge(ob_ctx* ctx, double* out, double* outge, const uint64_t* terms,
 int ob_getm(ob_ctx* ctx, double* out, const uint64_t* terms, uint64_t K, uint64_t d, const double* basemat, uint64_t N, uint64_t M,
             const double* basescale, const uint64_t* knotptst) {
   OB_TRY SEAM_BASE(nullptr, 0, nullptr, nullptr, 0) ob.getmat(terms, K, out); OB_CATCH
+}
+int ob_getmge(ob_ctx* ctx, double* outge, const uint64_t* terms, uint64_t K, uint64_t d, const double* basemat, uint64_t N, uint64_t M,
+              const double* basescale, const uint64_t* knotptst, const double* basematge, uint64_t Mge, const uint64_t* gest,
+              const uint64_t* hypmatch, uint64_t H) {
+  OB_TRY need(basematge, "basematge"); SEAM_BASE(basematge, Mge, gest, hypmatch, H) ob.getmat_gradhyp(terms, K, outge); OB_CATCH
 }
 
 /* ---- lpdf family */

@@ -673,6 +673,14 @@ struct OuterBase {
     obd::DevProgram* pr = program(terms, K, h < 0 ? -1 : (int)hypmatch[h]);
     obd::launch_getmat(ctx, plan(pr, 0, h), out_dev, ld);
   }
+  /* outerbase::getmat_gradhyp (modandbase.cpp:663-669; getmge_ linalg.cpp:778-822): N x K x H, slice after slice */
+  void getmat_gradhyp(const u64* terms, u64 K, double* out) {
+    tmpP.ensure(ld * std::max<u64>(K, 1));
+    for (u64 h = 0; h < H; ++h) {
+      getmat_dev(terms, K, (int)h, tmpP.p);
+      for (u64 k = 0; k < K; ++k) d2h(out + (h * K + k) * N, tmpP.p + k * ld, N);
+    }
+  }
   void getbase(u64 dim1, double* out) {
     if (dim1 < 1 || dim1 > d) throw std::range_error("dim out of range");
     ensure_all();

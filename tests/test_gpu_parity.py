@@ -384,6 +384,20 @@ def test_pruned_basis_layout_grows_with_the_terms(gpu, oracle):
     assert relerr(res["g"][1][3], res["o"][1][3]) < 1e-8 and relerr(res["g"][1][4], res["o"][1][4]) < 1e-7
 
 
+@pytest.mark.parametrize("N,K", [(200, 100), (10000, 100)])
+def test_getmge_seam_and_getmat_gradhyp(gpu, oracle, N, K):
+    """getmge_ (linalg.cpp:724-822) through the stateless seam on the oracle's basis, and outerbase::getmat_gradhyp
+    (modandbase.cpp:663-669) on the library's own: the factor of dimension hypmatch[h] replaced by its gradient column."""
+    o = oracle_basis(oracle, N, K)
+    terms = o["terms"]
+    want = oracle.getmge(terms, o["bm"], o["bs"], o["kp"], o["bg"], o["gest"], o["hm"])
+    got = gpu.getmge(terms, o["bm"], o["bs"], o["kp"], o["bg"], o["gest"], o["hm"])
+    assert got.shape == want.shape == (N, K, len(o["hm"]))
+    assert relerr(got, want) < MATVEC_TOL
+    omg, *_ = make_problem(gpu, N, K)
+    assert relerr(gpu.outerbase(omg, o["x"]).getmat_gradhyp(terms), o["ob"].getmat_gradhyp(terms)) < 1e-8  # own basis build
+
+
 @pytest.mark.parametrize("spec_mode", [1, 2])
 @pytest.mark.parametrize("N,K", [(200, 60), (600, 150), (20000, 100)])
 def test_loglik_std_optnewton_parity(gpu, oracle, N, K, spec_mode):

@@ -38,7 +38,7 @@ def test_shim_defines_every_function_of_linalg_h():
                "prodmmge_(", "tprodmmge_(", "getm_(", "getmge_("):
         assert fn in syms, fn
     undefined = subprocess.run(["nm", "-D", "--undefined-only", str(so)], capture_output=True, text=True, check=True).stdout
-    for fn in ("ob_prodmm_vec", "ob_tprodmm_vec", "ob_prodmm_mat", "ob_tprodmm_mat", "ob_prodmmge", "ob_tprodmmge", "ob_getm", "ob_ctx_create"):
+    for fn in ("ob_prodmm_vec", "ob_tprodmm_vec", "ob_prodmm_mat", "ob_tprodmm_mat", "ob_prodmmge", "ob_tprodmmge", "ob_getm", "ob_getmge", "ob_ctx_create"):
         assert fn in undefined, fn  # resolved by libouterbase_b200.so at load time
 
 
@@ -85,3 +85,26 @@ def test_reference_classes_on_gpu_kernels(gpu, N, K):
     assert relerr(g["coeff"], c["coeff"]) < tol and relerr(g["gradhyp"], c["gradhyp"]) < 1e3 * tol
     assert relerr(g["mean"], c["mean"]) < 10 * tol and relerr(g["var"], c["var"]) < 10 * tol
     assert gpu.launch_count() >= 0  # (the shim owns its own context; the fixture only guarantees a B200 is present)
+
+
+@pytest.mark.gpu
+def test_reference_loglik_std_on_gpu_kernels(gpu):
+    """The reference's own loglik_std + lpdfvec::optnewton (src/lpdfs/loglik_std.cpp, src/fit.cpp:98-131) with getm_ / getmge_ /
+    tprodmm_ forwarded to the CUDA kernels, against the same classes on the reference's CPU linalg.cpp -- getmge_ is the
+    eighth function of src/linalg.h.  N = 300 keeps the basis unchunked on any core count (the reference's chunked
+    getmge_ cannot work)."""
+    so_gpu, Library = _lib("libob_refgpu.so", "refgpu")
+    so_cpu, _ = _lib("libob_ref.so", "ref")
+    res = {}
+    for name, L in (("gpu", Library(so_gpu, "ref_")), ("cpu", Library(so_cpu, "ref_"))):
+        om, x, y, terms, rng = make_problem(L, 300, 50, covs=["mat25"] * 8, knots=[np.arange(0.001, 0.999, 0.05)] * 8)
+        ob = L.outerbase(om, x)
+        ob.nthreads = 1; ob.build()
+        cube = ob.getmat_gradhyp(terms)
+        lk, pr = L.loglik_std(om, terms, y, x), L.logpr_gauss(om, terms)
+        vec = L.lpdfvec(lk, pr)
+        vec.optnewton()
+        res[name] = dict(cube=cube, hess=lk.hess(), val=vec.val, coeff=np.array(vec.coeff), gradhyp=np.array(vec.gradhyp), gradpara=np.array(vec.gradpara))
+    assert relerr(res["gpu"]["cube"], res["cpu"]["cube"]) < 1e-12
+    for k in ("hess", "val", "coeff", "gradhyp", "gradpara"):
+        assert relerr(res["gpu"][k], res["cpu"][k]) < 1e-7, k

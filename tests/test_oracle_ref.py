@@ -318,6 +318,36 @@ def test_loglik_std_optnewton_full_hessian(oracle, reference, N, K):
 
 
 @pytest.mark.parametrize("N,K", [(200, 60), (600, 150)])
+def test_getmge_bitwise(oracle, reference, N, K):
+    """getmge_ (src/linalg.cpp:724-822, the eighth function of linalg.h) and outerbase::getmat_gradhyp on unchunked
+    bases: bit for bit on shared inputs; each slice is the derivative of getmat in one hyper-parameter (finite
+    differences of the basis)."""
+    o = both(oracle, reference, N, K, threads=1)
+    terms = o["terms"]
+    go, gr = o["obo"].getmat_gradhyp(terms), o["obr"].getmat_gradhyp(terms)
+    H = o["omo"].sizes()[1]
+    assert go.shape == (N, K, H)
+    np.testing.assert_array_equal(go, gr)
+    ob = o["obo"]
+    bm, bs, bg = ob.real("basemat"), ob.real("basescale"), ob.real("basemat_gradhyp")
+    kp, gest, hm = o["omo"].index("knotptst"), o["omo"].index("gest"), o["omo"].index("hypmatch")
+    so, sr = oracle.getmge(terms, bm, bs, kp, bg, gest, hm), reference.getmge(terms, bm, bs, kp, bg, gest, hm)
+    np.testing.assert_array_equal(so, sr)
+    np.testing.assert_array_equal(so, go)
+    # slice h against a central difference of getmat in hyper-parameter h
+    hyp = o["omo"].gethyp()
+    h, eps = 3, 1e-6
+    mats = []
+    for sgn in (+1, -1):
+        hp = hyp.copy(); hp[h] += sgn * eps
+        o["omo"].updatehyp(hp); ob.build()
+        mats.append(ob.getmat(terms))
+    o["omo"].updatehyp(hyp); ob.build()
+    fd = (mats[0] - mats[1]) / (2 * eps)
+    assert relerr(go[:, :, h], fd) < 1e-3  # sanity only: the reference differentiates its eigenbasis approximately
+
+
+@pytest.mark.parametrize("N,K", [(200, 60), (600, 150)])
 def test_loglik_std_matches_loglik_gauss(oracle, N, K):
     """The two likelihoods are the same model (vignettes/speed.Rmd:66): values, gradients and the diagonal of the Hessian
     of loglik_std agree with loglik_gauss's, and diag(hess) is diaghess."""
