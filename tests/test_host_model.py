@@ -84,3 +84,36 @@ def test_loopvals_rule():
     for N, T, cs in [(200, 8, 32), (10000, 8, 257), (1_000_000, 8, 257), (1_000_000, 64, 33)]:
         maxchunk = 1 + 2048 // T
         assert max(32, min(maxchunk, N // (4 * T) + 1)) == cs
+
+
+@pytest.mark.parametrize("K", [25, 120])
+def test_full_hessian_host_algebra_matches_oracle(product_symbols, oracle, K):
+    """The K x K side of the full-Hessian branch runs on the host in the product too, so it can be checked without a GPU:
+    logpr_gauss::hess / hessgradhyp / hessgradpara (logpr_gauss.cpp:153-186), lpdfvec's full branch of buildhess
+    (fit.cpp:269-299: log-determinant and inverse of the total Hessian -- Cholesky in the product, the reference's
+    eigen-decomposition in the oracle) and lpdf::optnewton (fit.cpp:98-131, elimination with partial pivoting) on
+    lpdfvec(logpr_gauss, logpr_gauss), a model whose every piece lives on the host."""
+    covs = ["mat25pow", "mat25", "mat25", "mat25pow"]
+    res = {}
+    for name, lib in (("p", product_symbols), ("o", oracle)):
+        om = build(lib, covs, 16, 0.2)
+        terms = om.selectterms(K)
+        a, b = lib.logpr_gauss(om, terms), lib.logpr_gauss(om, terms)
+        b.updatepara([5.0])
+        res[name] = dict(hess=a.hess(), hgh=a.hessgradhyp(), hgp=a.hessgradpara())
+        vec = lib.lpdfvec(a, b)
+        vec.set_coeff(0.3 * np.cos(np.arange(K)))
+        vec.optnewton()
+        res[name].update(val=vec.val, coeff=np.array(vec.coeff), gradhyp=np.array(vec.gradhyp), gradpara=np.array(vec.gradpara),
+                         tothess=vec.tothess, vhess=vec.hess(), vhgh=vec.hessgradhyp(), vhgp=vec.hessgradpara())
+        # the log-density is quadratic in the coefficients: one Newton step from anywhere lands on the optimum, 0
+        assert np.abs(vec.coeff).max() < 1e-12 and np.abs(vec.grad).max() < 1e-12
+        vec.optcg(0.001, 100)  # optcg switches back to the diagonal branch (fit.cpp:38)
+        vec.domarg = True
+    p, o = res["p"], res["o"]
+    for k in ("hess", "hgh", "hgp", "tothess", "vhess", "vhgh", "vhgp"):
+        np.testing.assert_array_equal(p[k], o[k], err_msg=k)
+    assert abs(p["val"] - o["val"]) <= 1e-12 * abs(o["val"])
+    for k in ("gradhyp", "gradpara"):
+        assert np.abs(p[k] - o[k]).max() <= 1e-11 * np.abs(o[k]).max(), k
+    assert p["hgh"].shape == (K, K, p["gradhyp"].size) and p["hgp"].shape == (K, K, 1) and p["vhgp"].shape == (K, K, 2)
