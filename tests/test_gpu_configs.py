@@ -1,7 +1,7 @@
 """GPU parity on the terms tables of the BASELINE configs themselves ("Untested configs").
 
 The shapes of tests/test_gpu_parity.py are the reference's test shapes (d = 8, K <= 2000).  Here the tables are the
-ones bench.py and the tools measure: C3 (d = 10, K = 2000, all mat25pow, 40 quantile knots: bench.setup_model),
+ones bench.py and the tools measure: C2 (d = 8, K = 1000), C3 (d = 10, K = 2000, all mat25pow, 40 quantile knots: bench.setup_model),
 C4 (d = 20, K = 4000) and C5 (C3's table with 64 right-hand sides), on a 20 000-row sample the oracle finishes in
 seconds, through the stateless linalg.h seam (bit-identical basemat from the oracle), BOTH kernel families
 (interpreter: spec = 0, terms-specialised: spec = 1).  Two tolerances per product:
@@ -34,6 +34,9 @@ def config_model(lib, cfg):
     if cfg in ("c3", "c5"):
         om, terms = bench.setup_model(lib)
         return om, terms, 10
+    if cfg == "c2":  # borehole d = 8, K = 1000 (bench.py --config c2)
+        om, terms = bench.config_model(lib, "c2")
+        return om, terms, 8
     assert cfg == "c4"
     from outerbase_b200 import fitting
     D, K = 20, 4000
@@ -51,7 +54,7 @@ def oracle_config(oracle, cfg, N):
     if key not in _CACHE:
         import bench
         om, terms, d = config_model(oracle, cfg)
-        x = bench.synth_rows(0, N, d, seed=42 if d == 10 else 7)
+        x = bench.synth_rows(0, N, d, seed=7 if d == 20 else 42)
         ob = oracle.outerbase(om, x)
         _CACHE.clear()  # one config resident at a time (C4: 20000 x 2400 doubles)
         _CACHE[key] = dict(om=om, terms=terms, x=x, ob=ob, bm=ob.real("basemat"), bs=ob.real("basescale"), bg=ob.real("basemat_gradhyp"),
@@ -69,9 +72,9 @@ def check(got, want, mag, norm_tol=NORM_TOL, elem_tol=ELEM_TOL, what=""):
 
 
 @pytest.mark.parametrize("family", ["interpreter", "specialised"])
-@pytest.mark.parametrize("cfg,N", [("c3", 20000), ("c4", 12000)])
+@pytest.mark.parametrize("cfg,N", [("c2", 20000), ("c3", 20000), ("c4", 12000)])
 def test_config_tables_against_the_oracle(gpu, oracle, cfg, N, family):
-    """prodmm_/tprodmm_/prodmmge_/tprodmmge_ (src/linalg.cpp:102-131, 303-355, 225-277, 394-471) on the C3 / C4 tables."""
+    """prodmm_/tprodmm_/prodmmge_/tprodmmge_ (src/linalg.cpp:102-131, 303-355, 225-277, 394-471) on the C2 / C3 / C4 tables."""
     o = oracle_config(oracle, cfg, N)
     terms, K = o["terms"], o["terms"].shape[0]
     rng = np.random.default_rng(3)
