@@ -84,3 +84,26 @@ def relerr(a, b):
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def one_cpu():
+    """The reference sizes its OpenMP teams with omp_get_num_procs() wherever a class builds its own outerbase
+    (modandbase.cpp:464: loglik_std's constructor, every predictor's update), and its short-basis branch races on basescale
+    when several threads run (modandbase.cpp:600-607, SURVEY A9-v: seen as a 0.5 % different 77-row basis once in a few
+    runs).  omp_get_num_procs() follows the CPU affinity of the process, so pinning the process to one CPU for the
+    duration makes those builds single-threaded and deterministic -- without touching the reference."""
+    import os
+    if not hasattr(os, "sched_setaffinity"):
+        yield
+        return
+    full = os.sched_getaffinity(0)
+    os.sched_setaffinity(0, {min(full)})
+    try:
+        yield
+    finally:
+        os.sched_setaffinity(0, full)
+

@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from conftest import REPO, make_problem, relerr
+from conftest import REPO, make_problem, one_cpu, relerr
 
 REFDIR = REPO / "oracle" / "_ref"
 REFSRC = Path("/root/reference/src")
@@ -61,9 +61,10 @@ def test_reference_classes_on_gpu_kernels(gpu, N, K):
         lk.setnthreads(1); lk.updateom()
         vec = L.lpdfvec(L.logpr_gauss(om, terms), lk)
         vec.optcg(0.001, 100)
-        pred = L.predictor(lk)
-        xn = np.asfortranarray(np.random.default_rng(5).uniform(size=(333, 8)))
-        pred.update(xn)
+        with one_cpu():  # predictor::update builds a 333-row basis with omp_get_num_procs() threads: the same race
+            pred = L.predictor(lk)
+            xn = np.asfortranarray(np.random.default_rng(5).uniform(size=(333, 8)))
+            pred.update(xn)
         res[name] = dict(bm=ob.real("basemat"), mm=ob.matmul(terms, a), tmm=ob.tmatmul(terms, r), mmge=ob.matmul_gradhyp(terms, a),
                          tmmge=ob.tmatmul_gradhyp(terms, r), sqcs=ob.sqcolsums(terms), mmat=ob.matmul(terms, A), tmat=ob.tmatmul(terms, Rm),
                          getmat=ob.getmat(terms) if N * K <= 2_000_000 else None, rv=ob.residvar(terms),
@@ -101,7 +102,8 @@ def test_reference_loglik_std_on_gpu_kernels(gpu):
         ob = L.outerbase(om, x)
         ob.nthreads = 1; ob.build()
         cube = ob.getmat_gradhyp(terms)
-        lk, pr = L.loglik_std(om, terms, y, x), L.logpr_gauss(om, terms)
+        with one_cpu():  # loglik_std builds its own basis with omp_get_num_procs() threads (no setnthreads): conftest.one_cpu
+            lk, pr = L.loglik_std(om, terms, y, x), L.logpr_gauss(om, terms)
         vec = L.lpdfvec(lk, pr)
         vec.optnewton()
         res[name] = dict(cube=cube, hess=lk.hess(), val=vec.val, coeff=np.array(vec.coeff), gradhyp=np.array(vec.gradhyp), gradpara=np.array(vec.gradpara))
