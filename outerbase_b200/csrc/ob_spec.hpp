@@ -714,7 +714,12 @@ inline SpecSource generate_mat(const Program& pa, const SpecOptions& opt) {
   tab.f("__device__ const unsigned short obs_cols_a[] = {");
   for (size_t c = 0; c < pa.cols.size(); ++c) tab.f("%d,", (int)c);
   tab.f("0};\n");
+  /* machine-readable layout (comments): tile column -> (dimension, level), emit slot -> term */
+  for (size_t c = 0; c < pa.cols.size(); ++c) tab.f("// OBS_LAYOUT_M %d %u %u\n", (int)c, pa.cols[c].dim, pa.cols[c].level);
+  for (u64 i = 0; i < pa.nslots(); ++i) tab.f("// OBS_SLOT_M %d %d\n", (int)i, (int)pa.slot_term[i]);
+  body.f("/*BEGIN_BODY_M*/\n");
   const int n = emit_mat(body, pa, S.tr_a, KC);
+  body.f("/*END_BODY_M*/\n");
   if (n != (int)pa.slot_real[0]) { S.why = "emit count mismatch"; return S; }
   S.nacc = (n + KC - 1) / KC; /* coefficient blocks per pass */
   hdr.f("#define OBS_NBLK %d\n#define OBS_KC %d\n#define OBS_MW %d\n", S.nacc, KC, MW);

@@ -147,6 +147,58 @@ def test_generated_statements_compute_phi(product_symbols, tmp_path):
     assert sorted(seen) == list(range(K))  # every term is owned by exactly one stream
 
 
+HARNESS_M = r"""
+#include <cstdint>
+static const double* TILE;
+static double PHI[64];
+static double* OUT;
+static inline double ldv(uint32_t a) { return TILE[a / 8]; }
+#define OBS_NBLK %(nblk)d
+#define OBS_M_EMIT(slot, value) PHI[slot] = (value)
+#define OBS_M_BLOCK() { for (int i = 0; i < %(kc)d; ++i) { OUT[blk * %(kc)d + i] = PHI[i]; PHI[i] = -1.0; } }
+extern "C" void run_m(const double* tile, double* out) {
+  TILE = tile; OUT = out;
+  const uint32_t tp = 0;
+  {
+%(body)s
+  }
+}
+"""
+
+
+@pytest.mark.parametrize("K,d", [(160, 8), (700, 10)])
+def test_generated_multi_rhs_emits_compute_phi(product_symbols, tmp_path, K, d):
+    """The forward program of phi_am_spec (blocks of KC emits with their basis-column loads hoisted to the top of the block,
+    ob_spec.hpp emit_mat): executed on the host for one random row, every emit slot holds Phi[row, term of the slot]
+    when its block is contracted, padding slots hold 0."""
+    terms, rng = _terms(product_symbols, K, d)
+    src, (nblk, tile_rows) = product_symbols.spec_source_mat(terms)
+    kc = int(re.search(r"#define OBS_KC (\d+)", src).group(1))
+    lay = [tuple(map(int, m)) for m in re.findall(r"// OBS_LAYOUT_M (\d+) (\d+) (\d+)", src)]
+    slots = [t for _, t in sorted(tuple(map(int, m)) for m in re.findall(r"// OBS_SLOT_M (\d+) (-?\d+)", src))]
+    body = re.search(r"/\*BEGIN_BODY_M\*/(.*?)/\*END_BODY_M\*/", src, re.S).group(1)
+    assert body.count("OBS_M_BLOCK()") == 1  # ONE shared instance of the contraction
+    cpp = tmp_path / "harness_m.cpp"
+    cpp.write_text(HARNESS_M % dict(nblk=nblk, kc=kc, body=body))
+    so = tmp_path / "harness_m.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), str(cpp)], check=True)
+    lib = C.CDLL(str(so))
+    L = int(terms.max()) + 1
+    B = rng.uniform(0.5, 1.5, size=(d, L))
+    phi = np.array([np.prod([B[l, terms[k, l]] for l in range(d) if terms[k, l] > 0]) for k in range(K)])
+    tile = np.zeros((len(lay) + 1) * tile_rows)
+    for pos, dim, lev in lay:
+        tile[pos * tile_rows] = B[dim, lev]
+    out = np.full(nblk * kc, np.nan)
+    lib.run_m(tile.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    real = [t for t in slots if t >= 0]
+    assert sorted(real) == list(range(K)) and len(slots) <= nblk * kc
+    for i in range(nblk * kc):
+        t = slots[i] if i < len(slots) else -1
+        want = phi[t] if t >= 0 else 0.0
+        assert abs(out[i] - want) <= 1e-13 * max(abs(want), 1.0), (i, t)
+
+
 HARNESS_D = r"""
 #include <cmath>
 #include <cstddef>
