@@ -775,11 +775,17 @@ inline SpecSource generate_tmat(const Program& pt, int types, const SpecOptions&
     const auto& tc = tcols[g / kTmWarps];
     std::vector<int> pos(pt.cols.size(), -1);
     for (size_t i = 0; i < tc.size(); ++i) pos[tc[i]] = (int)i;
-    ct.f("case %d: {\n", g);
+    ct.f("case %d: {\n/*BEGIN_CASE_TM %d*/\n", g, g);
     const int n = emit_fwd(ct, pt, g, 1, S.tr_t, 0, pos, /*park=*/true);
     if (n != (int)pt.slot_real[g]) { S.why = "emit count mismatch"; return S; }
-    ct.f("} break;\n");
+    ct.f("/*END_CASE_TM*/\n} break;\n");
+    /* machine-readable (comments): the terms of stream g in parking order */
+    tab.f("// OBS_STREAM_TM %d type %d terms", g, g / kTmWarps);
+    for (uint32_t i = 0; i < pt.slot_real[g]; ++i) tab.f(" %d", (int)pt.slot_term[pt.slot_base[g] + i]);
+    tab.f("\n");
   }
+  for (int t = 0; t < types; ++t) /* tile column of a type -> (dimension, level) */
+    for (size_t i = 0; i < tcols[t].size(); ++i) tab.f("// OBS_LAYOUT_TM %d %d %u %u\n", t, (int)i, pt.cols[tcols[t][i]].dim, pt.cols[tcols[t][i]].level);
   std::string src = scaffold_text();
   replace_marker(src, "//@@TABLES@@", tab.s);
   replace_marker(src, "//@@CASES_TM@@", ct.s);

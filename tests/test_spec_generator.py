@@ -199,6 +199,61 @@ def test_generated_multi_rhs_emits_compute_phi(product_symbols, tmp_path, K, d):
         assert abs(out[i] - want) <= 1e-13 * max(abs(want), 1.0), (i, t)
 
 
+HARNESS_TM = r"""
+#include <cstdint>
+static const double* TILE;
+static double* PHI;
+static inline double lds(uint32_t a) { return TILE[a / 8]; }
+static inline double ldv(uint32_t a) { return TILE[a / 8]; }
+#define OBS_TM_PARK(slot, value) PHI[slot] = (value)
+%(cases)s
+"""
+CASE_TM = r"""
+extern "C" void run_tm_%(g)d(const double* tile, double bval, double* phi) {
+  TILE = tile; PHI = phi;
+  const uint32_t tp = 0;
+  double b[1] = {bval};
+  {
+%(body)s
+  }
+}
+"""
+
+
+def test_generated_transposed_multi_rhs_parks_compute_phi(product_symbols, tmp_path):
+    """The streams of phi_tm_spec (forward program with every emit parked, ob_spec.hpp emit_fwd park = true): executed on
+    the host for one random row, stream g parks basescale * Phi[row, term] for its terms in order; every term belongs to
+    exactly one stream of at most 32."""
+    K, d = 300, 8
+    terms, rng = _terms(product_symbols, K, d)
+    src, info = product_symbols.spec_source_tmat(terms)
+    streams = {int(g): (int(t), [int(v) for v in rest.split()]) for g, t, rest in re.findall(r"// OBS_STREAM_TM (\d+) type (\d+) terms([ \d-]*)", src)}
+    lay = [tuple(map(int, m)) for m in re.findall(r"// OBS_LAYOUT_TM (\d+) (\d+) (\d+) (\d+)", src)]
+    cases = {int(g): body for g, body in re.findall(r"/\*BEGIN_CASE_TM (\d+)\*/(.*?)/\*END_CASE_TM\*/", src, re.S)}
+    assert len(cases) == len(streams) == info["types"] * 8
+    cpp = tmp_path / "harness_tm.cpp"
+    cpp.write_text(HARNESS_TM % dict(cases="".join(CASE_TM % dict(g=g, body=body) for g, body in cases.items())))
+    so = tmp_path / "harness_tm.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), str(cpp)], check=True)
+    lib = C.CDLL(str(so))
+    L = int(terms.max()) + 1
+    B = rng.uniform(0.5, 1.5, size=(d, L))
+    phi = np.array([np.prod([B[l, terms[k, l]] for l in range(d) if terms[k, l] > 0]) for k in range(K)])
+    TR, bval, seen = 64, 0.41, []
+    for g, (t, tlist) in streams.items():
+        assert len(tlist) <= 32
+        cols = [(pos, dim, lev) for (tt, pos, dim, lev) in lay if tt == t]
+        tile = np.zeros((len(cols) + 2) * TR)
+        for pos, dim, lev in cols:
+            tile[pos * TR] = B[dim, lev]
+        out = np.full(32, np.nan)
+        getattr(lib, f"run_tm_{g}")(tile.ctypes.data_as(C.c_void_p), C.c_double(bval), out.ctypes.data_as(C.c_void_p))
+        for i, k in enumerate(tlist):
+            assert abs(out[i] - bval * phi[k]) <= 1e-13 * abs(bval * phi[k]), (g, i, k)
+        seen += tlist
+    assert sorted(seen) == list(range(K))
+
+
 HARNESS_D = r"""
 #include <cmath>
 #include <cstddef>
